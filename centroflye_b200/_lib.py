@@ -1,0 +1,71 @@
+"""ctypes binding of libcfk.so (include/cfk.h).  There is no fallback: if the CUDA
+library is missing or an entry point fails, the caller gets an exception."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcfk.so")
+
+_p = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_i32 = ctypes.c_int32
+_u32 = ctypes.c_uint32
+_int = ctypes.c_int
+_f64 = ctypes.c_double
+
+# name -> (restype, argtypes); must list every symbol include/cfk.h declares
+# (tests/test_abi.py cross-checks this table against the header and the built library)
+SIGNATURES = {
+    "cfk_abi_version": (_int, []),
+    "cfk_last_error": (ctypes.c_char_p, []),
+    "cfk_dist_table_bytes_per_warp": (_int, []),
+    "cfk_launch_count": (_i64, []),
+    "cfk_docfreq_count": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _i64, _p, _i64, _p, _p]),
+    "cfk_table_merge": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p]),
+    "cfk_table_select": (_int, [_p, _p, _p, _i64, _u32, _u32, _u32, _i32, _i32, _p, _p, _p, _i64, _p, _p]),
+    "cfk_sort_u64": (_int, [_p, _i64, _p]),
+    "cfk_index_build": (_int, [_p, _i64, _p, _p, _i64, _p, _p]),
+    "cfk_cloud_build": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _i64, _p, _p, _p]),
+    "cfk_scan_scratch_elems": (_i64, [_i64]),
+    "cfk_exclusive_scan": (_int, [_p, _p, _i64, _p, _p]),
+    "cfk_cloud_compact": (_int, [_p, _p, _p, _i64, _p, _p]),
+    "cfk_id_histogram": (_int, [_p, _p, _i64, _i64, _p, _p]),
+    "cfk_cloud_filter_count": (_int, [_p, _p, _i64, _p, _i64, _i64, _p, _p]),
+    "cfk_cloud_filter_write": (_int, [_p, _p, _i64, _p, _i64, _i64, _p, _p, _p]),
+    "cfk_occ_fill": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p]),
+    "cfk_occ_sort": (_int, [_p, _p, _i64, _p]),
+    "cfk_dist_candidates": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p, _i32, _p]),
+    "cfk_edge_filter": (_int, [_p, _i64, _p, _p, _p, _i32, _i32, _f64, _p, _p, _p, _p]),
+    "cfk_flag_indices": (_int, [_p, _i64, _p, _p, _p]),
+}
+
+_lib = None
+
+
+class CfkError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libcfk.so once; raises if it has not been built (python -m centroflye_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CfkError(f"{LIB_PATH} is missing: build it with `python -m centroflye_b200.build` "
+                           "(there is no CPU fallback for the recruitment path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point; non-zero status -> CfkError with cfk_last_error()."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise CfkError(f"{name} failed ({rc}): {lib.cfk_last_error().decode(errors='replace')}")
+    return rc

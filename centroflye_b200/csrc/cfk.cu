@@ -1,0 +1,1026 @@
+// cfk.cu — sm_100a kernels + C ABI of the unique-k-mer recruitment path (see include/cfk.h).
+//
+// Everything here is integer / byte work bounded by HBM, L2 and shared-memory
+// throughput; there is no dense contraction, so no tensor-core (tcgen05) code.
+// Kernel-by-kernel rooflines and the HBM data layout are in DESIGN.md.
+//
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
+//             -shared -Xcompiler -fPIC -o libcfk.so cfk.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/cfk.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr uint64_t EMPTY = CFK_EMPTY_KEY;
+
+thread_local char g_err[512] = "";
+long long g_launches = 0;  // kernels enqueued through this library (bench.py reports it)
+
+int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (e != cudaSuccess)
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  else
+    snprintf(g_err, sizeof(g_err), "%s", what);
+  return code;
+}
+
+#define CFK_CHECK_LAUNCH(name, n_launched)                        \
+  do {                                                           \
+    cudaError_t e_ = cudaGetLastError();                         \
+    if (e_ != cudaSuccess) return fail(CFK_ERR_CUDA, name, e_);  \
+    __atomic_fetch_add(&g_launches, (long long)(n_launched), __ATOMIC_RELAXED); \
+  } while (0)
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+// home slot of a hashed key in a table of arbitrary capacity (multiply-shift range reduction)
+__device__ __forceinline__ int64_t home_slot(uint64_t h, int64_t cap) {
+  return (int64_t)__umul64hi(h, (uint64_t)cap);
+}
+
+__device__ __forceinline__ uint32_t base_at(const uint32_t* __restrict__ packed, int64_t pos) {
+  return (__ldg(packed + (pos >> 4)) >> ((pos & 15) << 1)) & 3u;
+}
+
+// find-or-insert in an open-addressing table of 64-bit keys; returns the slot or -1 if full
+__device__ __forceinline__ int64_t table_upsert(uint64_t* keys, int64_t cap, uint64_t key) {
+  int64_t slot = home_slot(mix64(key), cap);
+  for (int64_t probes = 0; probes < cap; ++probes) {
+    uint64_t cur = ((volatile uint64_t*)keys)[slot];
+    if (cur == key) return slot;
+    if (cur == EMPTY) {
+      unsigned long long old = atomicCAS((unsigned long long*)(keys + slot), (unsigned long long)EMPTY,
+                                         (unsigned long long)key);
+      if (old == EMPTY || old == key) return slot;
+    }
+    if (++slot == cap) slot = 0;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ int64_t table_find(const uint64_t* __restrict__ keys, int64_t cap, uint64_t key) {
+  int64_t slot = home_slot(mix64(key), cap);
+  for (int64_t probes = 0; probes < cap; ++probes) {
+    uint64_t cur = __ldg(keys + slot);
+    if (cur == key) return slot;
+    if (cur == EMPTY) return -1;
+    if (++slot == cap) slot = 0;
+  }
+  return -1;
+}
+
+// ============================================================================================
+// Stage A: document frequency.  One block = CFK_DOCFREQ_CHUNK consecutive k-mer starts of one
+// read, staged through shared memory; each thread rolls 8 consecutive k-mers.
+//   t1: kmer -> slot (dense id), with per-slot n_reads / n_multi
+//   t2: (slot, read) pair set, bit 0 = "seen twice in this read"
+// ============================================================================================
+constexpr int DF_THREADS = 256;
+constexpr int DF_PER_THREAD = CFK_DOCFREQ_CHUNK / DF_THREADS;
+constexpr int DF_WORDS = (CFK_DOCFREQ_CHUNK + 32 + 15) / 16 + 2;
+
+__global__ void __launch_bounds__(DF_THREADS)
+docfreq_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ read_off,
+               const int64_t* __restrict__ read_len, const int64_t* __restrict__ chunk_ptr, int64_t n_reads,
+               int64_t read_id_base, int k, uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti,
+               int64_t cap1, uint64_t* t2_pairs, int64_t cap2, int64_t* counters) {
+  __shared__ uint32_t s_words[DF_WORDS];
+  __shared__ int64_t s_read;
+  const int64_t chunk = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int64_t lo = 0, hi = n_reads;  // last r with chunk_ptr[r] <= chunk
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (chunk_ptr[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    s_read = lo;
+  }
+  __syncthreads();
+  const int64_t r = s_read;
+  const int64_t pos0 = (chunk - chunk_ptr[r]) * CFK_DOCFREQ_CHUNK;
+  const int64_t nk = read_len[r] - k + 1;
+  const int npos = (int)min((int64_t)CFK_DOCFREQ_CHUNK, nk - pos0);
+  if (npos <= 0) return;
+  const int64_t word0 = (read_off[r] + pos0) >> 4;  // read_off % 64 == 0 and pos0 % 2048 == 0
+  const int nwords = (npos + k - 1 + 15) >> 4;
+  for (int i = threadIdx.x; i < nwords; i += DF_THREADS) s_words[i] = __ldg(packed + word0 + i);
+  __syncthreads();
+
+  const int p0 = threadIdx.x * DF_PER_THREAD;
+  if (p0 >= npos) return;
+  const uint64_t mask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
+  const uint64_t read_bits = (uint64_t)(read_id_base + r) << 1;
+  uint64_t kmer = 0;
+  for (int i = 0; i < k - 1; ++i) {
+    int p = p0 + i;
+    kmer = (kmer << 2) | ((s_words[p >> 4] >> ((p & 15) << 1)) & 3u);
+  }
+  const int pend = min(p0 + DF_PER_THREAD, npos);
+  for (int p = p0; p < pend; ++p) {
+    int q = p + k - 1;
+    kmer = ((kmer << 2) | ((s_words[q >> 4] >> ((q & 15) << 1)) & 3u)) & mask;
+    int64_t slot = table_upsert(t1_keys, cap1, kmer);
+    if (slot < 0) { counters[0] = 1; return; }
+    const uint64_t pk = ((uint64_t)slot << 32) | read_bits;
+    int64_t s2 = home_slot(mix64(pk), cap2);
+    int64_t probes = 0;
+    for (; probes < cap2; ++probes) {
+      uint64_t cur = ((volatile uint64_t*)t2_pairs)[s2];
+      if (cur == EMPTY) {
+        unsigned long long old = atomicCAS((unsigned long long*)(t2_pairs + s2), (unsigned long long)EMPTY,
+                                           (unsigned long long)pk);
+        if (old == EMPTY) {  // first sighting of this k-mer in this read
+          atomicAdd(t1_nreads + slot, 1u);
+          break;
+        }
+        cur = old;
+      }
+      if ((cur & ~1ull) == pk) {
+        if (!(cur & 1ull)) {
+          unsigned long long old = atomicOr((unsigned long long*)(t2_pairs + s2), 1ull);
+          if (!(old & 1ull)) atomicAdd(t1_nmulti + slot, 1u);  // exactly one thread sees the 0 -> 1 flip
+        }
+        break;
+      }
+      if (++s2 == cap2) s2 = 0;
+    }
+    if (probes == cap2) { counters[1] = 1; return; }
+  }
+}
+
+__global__ void table_merge_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ nreads,
+                                   const uint32_t* __restrict__ nmulti, int64_t n, uint64_t* t1_keys,
+                                   uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1, int64_t* counters) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t slot = table_upsert(t1_keys, cap1, keys[i]);
+  if (slot < 0) { counters[0] = 1; return; }
+  if (nreads[i]) atomicAdd(t1_nreads + slot, nreads[i]);
+  if (nmulti[i]) atomicAdd(t1_nmulti + slot, nmulti[i]);
+}
+
+// warp-aggregated append: returns the output position of this lane's item, or -1
+__device__ __forceinline__ int64_t warp_append(bool take, int64_t* counter) {
+  unsigned m = __ballot_sync(FULL, take);
+  if (m == 0) return -1;
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd((unsigned long long*)counter, (unsigned long long)__popc(m));
+  base = __shfl_sync(FULL, base, leader);
+  return take ? (int64_t)base + __popc(m & ((1u << lane) - 1)) : -1;
+}
+
+__global__ void table_select_kernel(const uint64_t* __restrict__ t1_keys, const uint32_t* __restrict__ t1_nreads,
+                                    const uint32_t* __restrict__ t1_nmulti, int64_t cap1, uint32_t lo, uint32_t hi,
+                                    uint32_t max_nonuniq, int32_t n_parts, int32_t part, uint64_t* out_keys,
+                                    uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out, int64_t* counters) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool take = false;
+  uint64_t key = 0;
+  uint32_t nr = 0, nm = 0;
+  if (i < cap1) {
+    key = t1_keys[i];
+    if (key != EMPTY) {
+      nr = t1_nreads[i];
+      nm = t1_nmulti[i];
+      take = nm <= max_nonuniq && nr >= lo && nr <= hi;
+      if (take && n_parts > 0) take = (int32_t)(mix64(key ^ 0x9E3779B97F4A7C15ull) % (uint64_t)n_parts) == part;
+    }
+  }
+  int64_t pos = warp_append(take, counters);
+  if (take && pos < max_out) {
+    if (out_keys) out_keys[pos] = key;
+    if (out_nreads) out_nreads[pos] = nr;
+    if (out_nmulti) out_nmulti[pos] = nm;
+  }
+}
+
+// ============================================================================================
+// Bitonic sort of u64 keys ("flip / disperse" form: every compare-exchange is ascending, so
+// indices >= n behave as +inf padding without being stored).
+// ============================================================================================
+constexpr int SORT_TILE = 4096;
+constexpr int SORT_THREADS = 512;
+
+__device__ __forceinline__ void cmpx(uint64_t& a, uint64_t& b) {
+  if (b < a) { uint64_t t = a; a = b; b = t; }
+}
+
+// full == 1: sort each tile completely; full == 0: only the disperse steps hh = TILE/2 .. 1
+__global__ void __launch_bounds__(SORT_THREADS) sort_tile_kernel(uint64_t* d, int64_t n, int full) {
+  __shared__ uint64_t s[SORT_TILE];
+  const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+  for (int i = threadIdx.x; i < SORT_TILE; i += SORT_THREADS) s[i] = (base + i < n) ? d[base + i] : EMPTY;
+  __syncthreads();
+  if (full) {
+    for (int h = 1; h < SORT_TILE; h <<= 1) {
+      for (int i = threadIdx.x; i < SORT_TILE / 2; i += SORT_THREADS) {
+        int blk = i / h, off = i % h;
+        int lo = blk * 2 * h + off, hi = blk * 2 * h + 2 * h - 1 - off;
+        cmpx(s[lo], s[hi]);
+      }
+      __syncthreads();
+      for (int hh = h >> 1; hh >= 1; hh >>= 1) {
+        for (int i = threadIdx.x; i < SORT_TILE / 2; i += SORT_THREADS) {
+          int blk = i / hh, off = i % hh;
+          int lo = blk * 2 * hh + off;
+          cmpx(s[lo], s[lo + hh]);
+        }
+        __syncthreads();
+      }
+    }
+  } else {
+    for (int hh = SORT_TILE / 2; hh >= 1; hh >>= 1) {
+      for (int i = threadIdx.x; i < SORT_TILE / 2; i += SORT_THREADS) {
+        int blk = i / hh, off = i % hh;
+        int lo = blk * 2 * hh + off;
+        cmpx(s[lo], s[lo + hh]);
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < SORT_TILE; i += SORT_THREADS)
+    if (base + i < n) d[base + i] = s[i];
+}
+
+__global__ void sort_flip_kernel(uint64_t* d, int64_t n, int64_t h, int64_t n_pairs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  int64_t blk = i / h, off = i % h;
+  int64_t lo = blk * 2 * h + off, hi = blk * 2 * h + 2 * h - 1 - off;
+  if (hi < n) {
+    uint64_t a = d[lo], b = d[hi];
+    if (b < a) { d[lo] = b; d[hi] = a; }
+  }
+}
+
+__global__ void sort_disperse_kernel(uint64_t* d, int64_t n, int64_t hh, int64_t n_pairs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  int64_t blk = i / hh, off = i % hh;
+  int64_t lo = blk * 2 * hh + off, hi = lo + hh;
+  if (hi < n) {
+    uint64_t a = d[lo], b = d[hi];
+    if (b < a) { d[lo] = b; d[hi] = a; }
+  }
+}
+
+__global__ void index_build_kernel(const uint64_t* __restrict__ sorted_keys, int64_t n, uint64_t* idx_keys,
+                                   uint32_t* idx_vals, int64_t cap, int64_t* counters) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t slot = table_upsert(idx_keys, cap, sorted_keys[i]);
+  if (slot < 0) { counters[0] = 1; return; }
+  idx_vals[slot] = (uint32_t)i;
+}
+
+// ============================================================================================
+// Block-level helpers
+// ============================================================================================
+// ascending bitonic sort of data[0..n) (shared or global memory), all threads of the block
+__device__ void block_sort_u32(uint32_t* data, int n) {
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int h = 1; h < np2; h <<= 1) {
+    for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+      int blk = i / h, off = i % h;
+      int lo = blk * 2 * h + off, hi = blk * 2 * h + 2 * h - 1 - off;
+      if (hi < n) {
+        uint32_t a = data[lo], b = data[hi];
+        if (b < a) { data[lo] = b; data[hi] = a; }
+      }
+    }
+    __syncthreads();
+    for (int hh = h >> 1; hh >= 1; hh >>= 1) {
+      for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+        int blk = i / hh, off = i % hh;
+        int lo = blk * 2 * hh + off, hi = lo + hh;
+        if (hi < n) {
+          uint32_t a = data[lo], b = data[hi];
+          if (b < a) { data[lo] = b; data[hi] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// exclusive prefix sum of one int per thread across the block (blockDim.x <= 1024); also returns the total
+__device__ int block_exclusive_scan(int v, int* total, int* s_warp /* [32] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  int incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nwarps ? s_warp[lane] : 0;
+    int wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(FULL, wi, o);
+      if (lane >= o) wi += t;
+    }
+    s_warp[lane] = wi - w;  // exclusive warp offsets; lane 31 keeps grand total below
+    if (lane == 31) *total = wi;
+  }
+  __syncthreads();
+  int res = s_warp[warp] + incl - v;
+  __syncthreads();
+  return res;
+}
+
+// ============================================================================================
+// Stage B: one block per unit.  Probe every k-mer of the unit in the rare-set index, collect
+// hit ids, sort + unique them, write them to the unit's scratch run.
+// ============================================================================================
+constexpr int CL_THREADS = 256;
+constexpr int CL_RUN = 8;        // consecutive k-mer starts rolled by one thread
+constexpr int CL_SMEM_IDS = 8192;  // units with more k-mer starts than this sort in global scratch
+
+__global__ void __launch_bounds__(CL_THREADS)
+cloud_build_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ unit_off,
+                   const int32_t* __restrict__ unit_len, const int64_t* __restrict__ unit_kbase, int k,
+                   const uint64_t* __restrict__ idx_keys, const uint32_t* __restrict__ idx_vals, int64_t cap,
+                   uint32_t* tmp_ids, int32_t* unit_cnt) {
+  __shared__ uint32_t s_ids[CL_SMEM_IDS];
+  __shared__ int s_n;
+  __shared__ int s_total;
+  __shared__ int s_warp[32];
+  const int64_t u = blockIdx.x;
+  const int nk = unit_len[u] - k + 1;
+  if (nk <= 0) {
+    if (threadIdx.x == 0) unit_cnt[u] = 0;
+    return;
+  }
+  uint32_t* out = tmp_ids + unit_kbase[u];
+  uint32_t* list = (nk <= CL_SMEM_IDS) ? s_ids : out;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  const int64_t off = unit_off[u];
+  const uint64_t mask = (1ull << (2 * k)) - 1;
+  for (int p0 = threadIdx.x * CL_RUN; p0 < nk; p0 += CL_THREADS * CL_RUN) {
+    uint64_t kmer = 0;
+    for (int i = 0; i < k - 1; ++i) kmer = (kmer << 2) | base_at(packed, off + p0 + i);
+    const int pend = min(p0 + CL_RUN, nk);
+    for (int p = p0; p < pend; ++p) {
+      kmer = ((kmer << 2) | base_at(packed, off + p + k - 1)) & mask;
+      int64_t slot = table_find(idx_keys, cap, kmer);
+      if (slot >= 0) list[atomicAdd(&s_n, 1)] = __ldg(idx_vals + slot);
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n == 0) {
+    if (threadIdx.x == 0) unit_cnt[u] = 0;
+    return;
+  }
+  block_sort_u32(list, n);
+  // unique: keep the first of every run; tiles of blockDim elements, read phase / write phase
+  int written = 0;
+  for (int t0 = 0; t0 < n; t0 += CL_THREADS) {
+    int i = t0 + threadIdx.x;
+    uint32_t v = 0;
+    int keep = 0;
+    if (i < n) {
+      v = list[i];
+      keep = (i == 0) || (list[i - 1] != v);
+    }
+    __syncthreads();
+    int tile_total;
+    int pos = block_exclusive_scan(keep, &s_total, s_warp);
+    tile_total = s_total;
+    if (keep) out[written + pos] = v;
+    written += tile_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) unit_cnt[u] = written;
+}
+
+// ---- exclusive scan int32 -> int64 (3 phases) ------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const int32_t* __restrict__ in, int64_t n, int64_t* partial) {
+  __shared__ int64_t s[SCAN_THREADS / 32];
+  int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int64_t sum = 0;
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    int64_t i = base + j * SCAN_THREADS + threadIdx.x;
+    if (i < n) sum += in[i];
+  }
+  for (int o = 16; o >= 1; o >>= 1) sum += __shfl_down_sync(FULL, sum, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t t = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) t += s[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void scan_partials_kernel(int64_t* partial, int64_t nb) {
+  // single thread block, sequential over tiles of blockDim partials
+  __shared__ int64_t s[1024];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t t0 = 0; t0 < nb; t0 += blockDim.x) {
+    int64_t i = t0 + threadIdx.x;
+    int64_t v = i < nb ? partial[i] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+      int64_t t = threadIdx.x >= (unsigned)o ? s[threadIdx.x - o] : 0;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nb) partial[i] = carry + s[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += s[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int32_t* __restrict__ in, int64_t n,
+                                                                  const int64_t* __restrict__ partial, int64_t* out) {
+  // thread t owns SCAN_ITEMS consecutive inputs
+  __shared__ int64_t s_warp[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int32_t v[SCAN_ITEMS];
+  int64_t sum = 0;
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    v[j] = (base + j < n) ? in[base + j] : 0;
+    sum += v[j];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    int64_t t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int64_t woff = 0;
+  for (int w = 0; w < warp; ++w) woff += s_warp[w];
+  int64_t run = partial[blockIdx.x] + woff + incl - sum;
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    if (base + j < n) out[base + j + 1] = run + v[j];
+    run += v[j];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = 0;
+}
+
+__global__ void cloud_compact_kernel(const uint32_t* __restrict__ tmp_ids, const int64_t* __restrict__ unit_kbase,
+                                     const int64_t* __restrict__ unit_ptr, int64_t n_units, uint32_t* ids) {
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= n_units) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t dst = unit_ptr[u], cnt = unit_ptr[u + 1] - dst, src = unit_kbase[u];
+  for (int64_t i = lane; i < cnt; i += 32) ids[dst + i] = tmp_ids[src + i];
+}
+
+// ---- multiplicity histogram / filter / occurrence lists (warp per unit) ----------------------
+__global__ void id_histogram_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
+                                    int64_t unit_lo, int64_t unit_hi, int32_t* mult) {
+  const int64_t u = unit_lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (u >= unit_hi) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t e1 = unit_ptr[u + 1];
+  for (int64_t e = unit_ptr[u] + lane; e < e1; e += 32) atomicAdd(mult + ids[e], 1);
+}
+
+__global__ void cloud_filter_count_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
+                                          int64_t n_units, const int32_t* __restrict__ mult, int64_t min_mult,
+                                          int64_t max_mult, int32_t* new_cnt) {
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= n_units) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t e0 = unit_ptr[u], e1 = unit_ptr[u + 1];
+  int c = 0;
+  for (int64_t e = e0 + lane; e < e1; e += 32) {
+    int64_t m = mult[ids[e]];
+    c += (m >= min_mult && m <= max_mult);
+  }
+  for (int o = 16; o >= 1; o >>= 1) c += __shfl_down_sync(FULL, c, o);
+  if (lane == 0) new_cnt[u] = c;
+}
+
+__global__ void cloud_filter_write_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
+                                          int64_t n_units, const int32_t* __restrict__ mult, int64_t min_mult,
+                                          int64_t max_mult, const int64_t* __restrict__ new_ptr, uint32_t* new_ids) {
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (u >= n_units) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t e0 = unit_ptr[u], e1 = unit_ptr[u + 1];
+  int64_t dst = new_ptr[u];
+  for (int64_t eb = e0; eb < e1; eb += 32) {  // order-preserving (ids stay sorted inside the unit)
+    int64_t e = eb + lane;
+    uint32_t id = 0;
+    bool keep = false;
+    if (e < e1) {
+      id = ids[e];
+      int64_t m = mult[id];
+      keep = m >= min_mult && m <= max_mult;
+    }
+    unsigned bal = __ballot_sync(FULL, keep);
+    if (keep) new_ids[dst + __popc(bal & ((1u << lane) - 1))] = id;
+    dst += __popc(bal);
+  }
+}
+
+__global__ void occ_fill_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
+                                int64_t unit_lo, int64_t unit_hi, const int64_t* __restrict__ occ_ptr,
+                                int32_t* cursor, uint32_t* occ) {
+  const int64_t u = unit_lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (u >= unit_hi) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t e1 = unit_ptr[u + 1];
+  for (int64_t e = unit_ptr[u] + lane; e < e1; e += 32) {
+    uint32_t id = ids[e];
+    occ[occ_ptr[id] + atomicAdd(cursor + id, 1)] = (uint32_t)u;
+  }
+}
+
+__global__ void occ_sort_kernel(const int64_t* __restrict__ occ_ptr, uint32_t* occ, int64_t n_kmers) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_kmers) return;
+  const int64_t b = occ_ptr[a], m = occ_ptr[a + 1] - b;
+  for (int64_t i = 1; i < m; ++i) {  // insertion sort; lists are a few dozen entries
+    uint32_t v = occ[b + i];
+    int64_t j = i - 1;
+    while (j >= 0 && occ[b + j] > v) { occ[b + j + 1] = occ[b + j]; --j; }
+    occ[b + j + 1] = v;
+  }
+}
+
+// ============================================================================================
+// Stage C: pair counting.  One warp per source id a; for every distance d it merges the cloud
+// id lists of the units d after each occurrence of a into a warp-private shared-memory
+// table  slot = (b + 1) << cb | count  (count <= #occurrences, so cb = bits(m) suffices).
+// Lanes of one insert step hold ids of ONE sorted-unique list, i.e. distinct keys, so the
+// insert needs no atomics: claim by plain store, re-read after __syncwarp, loser moves on.
+// ============================================================================================
+constexpr int DC_WARPS = 8;
+constexpr int DC_TBL_BYTES = 16384;
+
+// inserts key b (if valid) into the warp's table; returns the number of NEW distinct keys (uniform)
+template <typename S>
+__device__ __forceinline__ int warp_insert(volatile S* tbl, uint32_t b, bool valid, int cb) {
+  constexpr int NS = DC_TBL_BYTES / (int)sizeof(S);
+  constexpr int LOG_NS = (NS == 4096) ? 12 : 11;
+  static_assert(NS == 4096 || NS == 2048, "table geometry");
+  const S key = (S)b + 1;
+  uint32_t h = (b * 2654435761u) >> (32 - LOG_NS);
+  bool pending = valid;
+  int fresh = 0;
+  while (__any_sync(FULL, pending)) {
+    bool claimed = false;
+    if (pending) {
+      S w = tbl[h];
+      if (w == 0) {
+        tbl[h] = (key << cb) | 1;
+        claimed = true;
+      } else if ((w >> cb) == key) {
+        tbl[h] = w + 1;
+        pending = false;
+      } else {
+        h = (h + 1) & (NS - 1);
+      }
+    }
+    __syncwarp();
+    bool won = false;
+    if (claimed) {
+      S w = tbl[h];
+      if ((w >> cb) == key) { pending = false; won = true; }
+      else h = (h + 1) & (NS - 1);
+    }
+    fresh += __popc(__ballot_sync(FULL, won));
+    __syncwarp();
+  }
+  return fresh;
+}
+
+__device__ __forceinline__ int64_t lower_bound_ids(const uint32_t* __restrict__ ids, int64_t lo, int64_t hi, uint32_t v) {
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg(ids + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <typename S>
+__device__ void dist_one_distance(volatile S* tbl, const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
+                                  const uint32_t* __restrict__ unit_last, const uint32_t* __restrict__ occ_a, int64_t m,
+                                  uint32_t a, int d, int cb, int64_t n_kmers, uint32_t min_cov, uint4* cand,
+                                  int64_t max_cand, int64_t* counters, int64_t& incr_total, int64_t& splits) {
+  constexpr int NS = DC_TBL_BYTES / (int)sizeof(S);
+  constexpr int MAXLOAD = NS * 3 / 4;
+  const int lane = threadIdx.x & 31;
+  // how many list entries does this distance touch?
+  int64_t total = 0;
+  for (int64_t t0 = 0; t0 < m; t0 += 32) {
+    int64_t t = t0 + lane;
+    if (t < m) {
+      uint32_t g = __ldg(occ_a + t);
+      if ((int64_t)g + d <= (int64_t)__ldg(unit_last + g)) total += unit_ptr[g + d + 1] - unit_ptr[g + d];
+    }
+  }
+  for (int o = 16; o >= 1; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+  if (total == 0) return;
+  int64_t width = n_kmers;
+  if (total > MAXLOAD) {
+    int64_t parts = (total + NS / 2 - 1) / (NS / 2);
+    width = max((int64_t)1, n_kmers / parts);
+  }
+  const S cmask = ((S)1 << cb) - 1;
+  int64_t lo = 0;
+  while (lo < n_kmers) {
+    const int64_t hi = min(n_kmers, lo + width);
+    const bool whole = (lo == 0 && hi == n_kmers);
+    {
+      uint4* clr = reinterpret_cast<uint4*>(const_cast<S*>(tbl));
+      for (int i = lane; i < DC_TBL_BYTES / 16; i += 32) clr[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+    int distinct = 0;
+    int64_t incr = 0;
+    bool overflow = false;
+    for (int64_t t0 = 0; t0 < m && !overflow; t0 += 32) {
+      int64_t t = t0 + lane;
+      int64_t beg = 0, end = 0;
+      if (t < m) {
+        uint32_t g = __ldg(occ_a + t);
+        if ((int64_t)g + d <= (int64_t)__ldg(unit_last + g)) {
+          beg = unit_ptr[g + d];
+          end = unit_ptr[g + d + 1];
+          if (!whole && end > beg) {
+            int64_t nb = lower_bound_ids(ids, beg, end, (uint32_t)lo);
+            end = (hi >= n_kmers) ? end : lower_bound_ids(ids, nb, end, (uint32_t)hi);
+            beg = nb;
+          }
+        }
+      }
+      unsigned lists = __ballot_sync(FULL, end > beg);
+      while (lists && !overflow) {
+        const int src = __ffs(lists) - 1;
+        lists &= lists - 1;
+        const int64_t b0 = __shfl_sync(FULL, beg, src), e0 = __shfl_sync(FULL, end, src);
+        for (int64_t p = b0; p < e0; p += 32) {
+          const int64_t idx = p + lane;
+          bool valid = idx < e0;
+          uint32_t b = valid ? __ldg(ids + idx) : 0u;
+          valid = valid && (b != a);
+          incr += __popc(__ballot_sync(FULL, valid));
+          distinct += warp_insert<S>(tbl, b, valid, cb);
+          if (distinct > MAXLOAD) { overflow = true; break; }
+        }
+      }
+    }
+    if (overflow && width > 1) {  // too many distinct ids for one table: halve the id range and redo it
+      width = max((int64_t)1, width >> 1);
+      ++splits;
+      continue;
+    }
+    // emit (a, b, d, cnt) for every key that reached min_cov
+    for (int i = lane; i < NS; i += 32) {
+      S w = tbl[i];
+      uint32_t cnt = (uint32_t)(w & cmask);
+      bool take = (w != 0) && cnt >= min_cov;
+      int64_t pos = warp_append(take, counters);
+      if (take && pos < max_cand) cand[pos] = make_uint4(a, (uint32_t)(w >> cb) - 1u, (uint32_t)d, cnt);
+    }
+    incr_total += incr;
+    lo = hi;
+  }
+}
+
+__global__ void __launch_bounds__(DC_WARPS * 32)
+dist_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
+                       const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
+                       const uint32_t* __restrict__ occ, int64_t n_kmers, int64_t a_begin, int64_t a_end,
+                       int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint4* cand,
+                       int64_t max_cand, int64_t* counters) {
+  extern __shared__ __align__(16) unsigned char dc_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* my_tbl = dc_smem + (size_t)warp * DC_TBL_BYTES;
+  const int dmin = max(min_d, 1);
+  int64_t incr_total = 0, splits = 0;
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd((unsigned long long*)(counters + 1), 1ull);
+    item = __shfl_sync(FULL, item, 0);
+    const int64_t a64 = a_begin + (int64_t)item * a_stride;
+    if (a64 >= a_end) break;
+    const uint32_t a = (uint32_t)a64;
+    const int64_t o0 = occ_ptr[a], m = occ_ptr[a + 1] - o0;
+    if (m == 0) continue;
+    const uint32_t* occ_a = occ + o0;
+    int64_t maxrem = 0;
+    for (int64_t t0 = 0; t0 < m; t0 += 32) {
+      int64_t t = t0 + lane;
+      if (t < m) {
+        uint32_t g = __ldg(occ_a + t);
+        maxrem = max(maxrem, (int64_t)__ldg(unit_last + g) - (int64_t)g);
+      }
+    }
+    for (int o = 16; o >= 1; o >>= 1) maxrem = max(maxrem, __shfl_xor_sync(FULL, maxrem, o));
+    const int dmax = (int)min((int64_t)max_d, maxrem);
+    const int cb = 64 - __clzll((unsigned long long)m);  // counts never exceed m
+    const bool narrow = cb < 32 && ((uint64_t)n_kmers + 1) <= (1ull << (32 - cb));
+    for (int d = dmin; d <= dmax; ++d) {
+      if (narrow)
+        dist_one_distance<uint32_t>((volatile uint32_t*)my_tbl, unit_ptr, ids, unit_last, occ_a, m, a, d, cb,
+                                    n_kmers, min_cov, cand, max_cand, counters, incr_total, splits);
+      else
+        dist_one_distance<uint64_t>((volatile uint64_t*)my_tbl, unit_ptr, ids, unit_last, occ_a, m, a, d, 32,
+                                    n_kmers, min_cov, cand, max_cand, counters, incr_total, splits);
+    }
+  }
+  if (lane == 0) {
+    if (incr_total) atomicAdd((unsigned long long*)(counters + 2), (unsigned long long)incr_total);
+    if (splits) atomicAdd((unsigned long long*)(counters + 3), (unsigned long long)splits);
+  }
+}
+
+// ============================================================================================
+// Stage D: one thread per candidate; all_occ by joining the two sorted occurrence lists.
+// ============================================================================================
+__global__ void edge_filter_kernel(const uint4* __restrict__ cand, int64_t n_cand, const int64_t* __restrict__ occ_ptr,
+                                   const uint32_t* __restrict__ occ, const uint32_t* __restrict__ unit_last,
+                                   int32_t min_d, int32_t max_d, double rel_threshold, uint4* edges,
+                                   uint8_t* selected, int64_t* counters) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool keep = false;
+  uint4 c = make_uint4(0, 0, 0, 0);
+  if (i < n_cand) {
+    c = cand[i];
+    const int64_t a0 = occ_ptr[c.x], a1 = occ_ptr[c.x + 1];
+    const int64_t b0 = occ_ptr[c.y], b1 = occ_ptr[c.y + 1];
+    const int dmin = max(min_d, 1);
+    uint64_t all_occ = 0;
+    for (int64_t t = a0; t < a1; ++t) {
+      const int64_t g = __ldg(occ + t);
+      const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, (int64_t)__ldg(unit_last + g));
+      if (lo > hi) continue;
+      int64_t l = b0, r = b1;  // first occ(b) >= lo
+      while (l < r) { int64_t mid = (l + r) >> 1; if ((int64_t)__ldg(occ + mid) < lo) l = mid + 1; else r = mid; }
+      int64_t first = l;
+      r = b1;                  // first occ(b) > hi
+      while (l < r) { int64_t mid = (l + r) >> 1; if ((int64_t)__ldg(occ + mid) <= hi) l = mid + 1; else r = mid; }
+      all_occ += (uint64_t)(l - first);
+    }
+    keep = all_occ > 0 && ((double)c.w / (double)all_occ) >= rel_threshold;
+  }
+  int64_t pos = warp_append(keep, counters);
+  if (keep) {
+    edges[pos] = c;
+    selected[c.x] = 1;
+    selected[c.y] = 1;
+  }
+}
+
+__global__ void flag_indices_kernel(const uint8_t* __restrict__ flags, int64_t n, uint32_t* out, int64_t* counters) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool take = i < n && flags[i] != 0;
+  int64_t pos = warp_append(take, counters);
+  if (take) out[pos] = (uint32_t)i;
+}
+
+inline int64_t blocks_for(int64_t n, int threads) { return (n + threads - 1) / threads; }
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int cfk_abi_version(void) { return 1; }
+const char* cfk_last_error(void) { return g_err; }
+int cfk_dist_table_bytes_per_warp(void) { return DC_TBL_BYTES; }
+int64_t cfk_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len,
+                      const int64_t* chunk_ptr, int64_t n_reads, int64_t n_chunks, int64_t read_id_base, int k,
+                      uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1,
+                      uint64_t* t2_pairs, int64_t cap2, int64_t* counters, cfk_stream_t stream) {
+  if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_docfreq_count: k must be in [1, 31]");
+  if (cap1 < 1 || cap1 >= (1ll << 31) || cap2 < 1)
+    return fail(CFK_ERR_INVALID, "cfk_docfreq_count: need 1 <= cap1 < 2^31 and cap2 >= 1");
+  if (n_reads < 0 || read_id_base < 0 || read_id_base + n_reads >= (1ll << 31))
+    return fail(CFK_ERR_INVALID, "cfk_docfreq_count: read ids must stay below 2^31");
+  if (n_chunks >= (1ll << 31)) return fail(CFK_ERR_INVALID, "cfk_docfreq_count: too many chunks for one launch");
+  if (n_reads == 0 || n_chunks == 0) return CFK_OK;
+  docfreq_kernel<<<(unsigned)n_chunks, DF_THREADS, 0, (cudaStream_t)stream>>>(
+      packed, read_off, read_len, chunk_ptr, n_reads, read_id_base, k, t1_keys, t1_nreads, t1_nmulti, cap1, t2_pairs,
+      cap2, counters);
+  CFK_CHECK_LAUNCH("docfreq_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n,
+                    uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1, int64_t* counters,
+                    cfk_stream_t stream) {
+  if (n < 0 || cap1 < 1) return fail(CFK_ERR_INVALID, "cfk_table_merge: bad sizes");
+  if (n == 0) return CFK_OK;
+  table_merge_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, nreads, nmulti, n, t1_keys,
+                                                                                      t1_nreads, t1_nmulti, cap1, counters);
+  CFK_CHECK_LAUNCH("table_merge_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_table_select(const uint64_t* t1_keys, const uint32_t* t1_nreads, const uint32_t* t1_nmulti, int64_t cap1,
+                     uint32_t lo, uint32_t hi, uint32_t max_nonuniq, int32_t n_parts, int32_t part,
+                     uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out,
+                     int64_t* counters, cfk_stream_t stream) {
+  if (cap1 < 1 || max_out < 0) return fail(CFK_ERR_INVALID, "cfk_table_select: bad sizes");
+  if (n_parts > 0 && (part < 0 || part >= n_parts)) return fail(CFK_ERR_INVALID, "cfk_table_select: bad partition");
+  table_select_kernel<<<(unsigned)blocks_for(cap1, 256), 256, 0, (cudaStream_t)stream>>>(
+      t1_keys, t1_nreads, t1_nmulti, cap1, lo, hi, max_nonuniq, n_parts, part, out_keys, out_nreads, out_nmulti, max_out,
+      counters);
+  CFK_CHECK_LAUNCH("table_select_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_sort_u64(uint64_t* keys, int64_t n, cfk_stream_t stream) {
+  if (n < 0) return fail(CFK_ERR_INVALID, "cfk_sort_u64: n < 0");
+  if (n <= 1) return CFK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t np2 = SORT_TILE;
+  while (np2 < n) np2 <<= 1;
+  const unsigned tiles = (unsigned)blocks_for(n, SORT_TILE);
+  sort_tile_kernel<<<tiles, SORT_THREADS, 0, st>>>(keys, n, 1);
+  CFK_CHECK_LAUNCH("sort_tile_kernel", 1);
+  const int64_t n_pairs = np2 / 2;
+  int launched = 0;
+  for (int64_t h = SORT_TILE; h < np2; h <<= 1) {
+    sort_flip_kernel<<<(unsigned)blocks_for(n_pairs, 256), 256, 0, st>>>(keys, n, h, n_pairs);
+    ++launched;
+    for (int64_t hh = h >> 1; hh >= SORT_TILE; hh >>= 1, ++launched)
+      sort_disperse_kernel<<<(unsigned)blocks_for(n_pairs, 256), 256, 0, st>>>(keys, n, hh, n_pairs);
+    sort_tile_kernel<<<tiles, SORT_THREADS, 0, st>>>(keys, n, 0);
+    ++launched;
+  }
+  CFK_CHECK_LAUNCH("sort_u64", launched);
+  return CFK_OK;
+}
+
+int cfk_index_build(const uint64_t* sorted_keys, int64_t n, uint64_t* idx_keys, uint32_t* idx_vals, int64_t cap,
+                    int64_t* counters, cfk_stream_t stream) {
+  if (n < 0 || cap < 1 || n >= (1ll << 32) - 1) return fail(CFK_ERR_INVALID, "cfk_index_build: bad sizes");
+  if (n == 0) return CFK_OK;
+  index_build_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(sorted_keys, n, idx_keys, idx_vals,
+                                                                                      cap, counters);
+  CFK_CHECK_LAUNCH("index_build_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_cloud_build(const uint32_t* packed, const int64_t* unit_off, const int32_t* unit_len,
+                    const int64_t* unit_kbase, int64_t n_units, int k, const uint64_t* idx_keys,
+                    const uint32_t* idx_vals, int64_t cap, uint32_t* tmp_ids, int32_t* unit_cnt, cfk_stream_t stream) {
+  if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_cloud_build: k must be in [1, 31]");
+  if (n_units < 0 || n_units >= (1ll << 31) || cap < 1) return fail(CFK_ERR_INVALID, "cfk_cloud_build: bad sizes");
+  if (n_units == 0) return CFK_OK;
+  cloud_build_kernel<<<(unsigned)n_units, CL_THREADS, 0, (cudaStream_t)stream>>>(packed, unit_off, unit_len, unit_kbase, k,
+                                                                                 idx_keys, idx_vals, cap, tmp_ids, unit_cnt);
+  CFK_CHECK_LAUNCH("cloud_build_kernel", 1);
+  return CFK_OK;
+}
+
+int64_t cfk_scan_scratch_elems(int64_t n) { return blocks_for(n > 0 ? n : 1, SCAN_TILE) + 1; }
+
+int cfk_exclusive_scan(const int32_t* in, int64_t* out, int64_t n, int64_t* scratch, cfk_stream_t stream) {
+  if (n < 0) return fail(CFK_ERR_INVALID, "cfk_exclusive_scan: n < 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(int64_t), st);
+    if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_exclusive_scan memset", e);
+    return CFK_OK;
+  }
+  const int64_t nb = blocks_for(n, SCAN_TILE);
+  scan_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, scratch);
+  scan_partials_kernel<<<1, 1024, 0, st>>>(scratch, nb);
+  scan_apply_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, scratch, out);
+  CFK_CHECK_LAUNCH("exclusive_scan", 3);
+  return CFK_OK;
+}
+
+int cfk_cloud_compact(const uint32_t* tmp_ids, const int64_t* unit_kbase, const int64_t* unit_ptr, int64_t n_units,
+                      uint32_t* ids, cfk_stream_t stream) {
+  if (n_units < 0) return fail(CFK_ERR_INVALID, "cfk_cloud_compact: n_units < 0");
+  if (n_units == 0) return CFK_OK;
+  cloud_compact_kernel<<<(unsigned)blocks_for(n_units * 32, 256), 256, 0, (cudaStream_t)stream>>>(tmp_ids, unit_kbase,
+                                                                                                  unit_ptr, n_units, ids);
+  CFK_CHECK_LAUNCH("cloud_compact_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_id_histogram(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, int64_t unit_hi, int32_t* mult,
+                     cfk_stream_t stream) {
+  if (unit_lo < 0 || unit_hi < unit_lo) return fail(CFK_ERR_INVALID, "cfk_id_histogram: bad unit range");
+  if (unit_hi == unit_lo) return CFK_OK;
+  id_histogram_kernel<<<(unsigned)blocks_for((unit_hi - unit_lo) * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      unit_ptr, ids, unit_lo, unit_hi, mult);
+  CFK_CHECK_LAUNCH("id_histogram_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_cloud_filter_count(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, const int32_t* mult,
+                           int64_t min_mult, int64_t max_mult, int32_t* new_cnt, cfk_stream_t stream) {
+  if (n_units < 0) return fail(CFK_ERR_INVALID, "cfk_cloud_filter_count: n_units < 0");
+  if (n_units == 0) return CFK_OK;
+  cloud_filter_count_kernel<<<(unsigned)blocks_for(n_units * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      unit_ptr, ids, n_units, mult, min_mult, max_mult, new_cnt);
+  CFK_CHECK_LAUNCH("cloud_filter_count_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_cloud_filter_write(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, const int32_t* mult,
+                           int64_t min_mult, int64_t max_mult, const int64_t* new_ptr, uint32_t* new_ids,
+                           cfk_stream_t stream) {
+  if (n_units < 0) return fail(CFK_ERR_INVALID, "cfk_cloud_filter_write: n_units < 0");
+  if (n_units == 0) return CFK_OK;
+  cloud_filter_write_kernel<<<(unsigned)blocks_for(n_units * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      unit_ptr, ids, n_units, mult, min_mult, max_mult, new_ptr, new_ids);
+  CFK_CHECK_LAUNCH("cloud_filter_write_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_occ_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, int64_t unit_hi,
+                 const int64_t* occ_ptr, int32_t* cursor, uint32_t* occ, cfk_stream_t stream) {
+  if (unit_lo < 0 || unit_hi < unit_lo) return fail(CFK_ERR_INVALID, "cfk_occ_fill: bad unit range");
+  if (unit_hi == unit_lo) return CFK_OK;
+  occ_fill_kernel<<<(unsigned)blocks_for((unit_hi - unit_lo) * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      unit_ptr, ids, unit_lo, unit_hi, occ_ptr, cursor, occ);
+  CFK_CHECK_LAUNCH("occ_fill_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_stream_t stream) {
+  if (n_kmers < 0) return fail(CFK_ERR_INVALID, "cfk_occ_sort: n_kmers < 0");
+  if (n_kmers == 0) return CFK_OK;
+  occ_sort_kernel<<<(unsigned)blocks_for(n_kmers, 128), 128, 0, (cudaStream_t)stream>>>(occ_ptr, occ, n_kmers);
+  CFK_CHECK_LAUNCH("occ_sort_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_dist_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint32_t* unit_last,
+                        const int64_t* occ_ptr, const uint32_t* occ, int64_t n_kmers, int64_t a_begin, int64_t a_end,
+                        int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint32_t* cand,
+                        int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream) {
+  if (n_kmers < 0 || n_kmers >= (1ll << 32) - 1) return fail(CFK_ERR_INVALID, "cfk_dist_candidates: bad n_kmers");
+  if (min_d < 0) return fail(CFK_ERR_INVALID, "cfk_dist_candidates: min_d < 0 is not defined by the reference loop");
+  if (a_begin < 0 || a_end > n_kmers || a_stride < 1) return fail(CFK_ERR_INVALID, "cfk_dist_candidates: bad id range");
+  if (max_cand < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_dist_candidates: bad sizes");
+  if (a_begin >= a_end || max_d < (min_d > 1 ? min_d : 1)) return CFK_OK;
+  static bool attr_done = false;
+  const int smem = DC_WARPS * DC_TBL_BYTES;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(dist_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_dist_candidates: cudaFuncSetAttribute", e);
+    attr_done = true;
+  }
+  dist_candidates_kernel<<<(unsigned)n_blocks, DC_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      unit_ptr, ids, unit_last, occ_ptr, occ, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
+      max_cand, counters);
+  CFK_CHECK_LAUNCH("dist_candidates_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_edge_filter(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ,
+                    const uint32_t* unit_last, int32_t min_d, int32_t max_d, double rel_threshold, uint32_t* edges,
+                    uint8_t* selected, int64_t* counters, cfk_stream_t stream) {
+  if (n_cand < 0) return fail(CFK_ERR_INVALID, "cfk_edge_filter: n_cand < 0");
+  if (n_cand == 0) return CFK_OK;
+  edge_filter_kernel<<<(unsigned)blocks_for(n_cand, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)cand, n_cand, occ_ptr, occ, unit_last, min_d, max_d, rel_threshold, (uint4*)edges, selected, counters);
+  CFK_CHECK_LAUNCH("edge_filter_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_flag_indices(const uint8_t* flags, int64_t n, uint32_t* out, int64_t* counters, cfk_stream_t stream) {
+  if (n < 0) return fail(CFK_ERR_INVALID, "cfk_flag_indices: n < 0");
+  if (n == 0) return CFK_OK;
+  flag_indices_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(flags, n, out, counters);
+  CFK_CHECK_LAUNCH("flag_indices_kernel", 1);
+  return CFK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,398 @@
+"""Device pipeline of the recruitment path: PyTorch owns memory and streams, libcfk.so does the work.
+
+Stages (reference function each one replaces, paths under /root/reference/scripts):
+
+  count_docfreq   get_kmer_freqs_from_ncrf_report   distance_based_kmer_recruitment.py:39-63
+  select / index  get_rare_kmers band + kmer_index  distance_based_kmer_recruitment.py:74-79,103
+  build_clouds    ReadKMerCloud.fromNCRF_record     read_kmer_cloud.py:18-31
+  filter_clouds   filter_reads_kmer_clouds          read_kmer_cloud.py:43-54
+  dist_edges      get_kmer_dist_map + filter_dist_tuples  distance_based_kmer_recruitment.py:85-149
+
+There is no CPU fallback: constructing an Engine without CUDA or without libcfk.so raises.
+"""
+import contextlib
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import CfkError
+from .encode import check_k
+
+DOCFREQ_CHUNK = 2048
+U32_MAX = 0xFFFFFFFF
+
+
+def band_to_int(left, right):
+    """Integer form of ``left <= freq <= right`` for integer freq (floats come from dbkr.py:74-75)."""
+    lo = max(0, math.ceil(left))
+    hi = math.floor(right)
+    return lo, min(hi, U32_MAX)
+
+
+@dataclass
+class DeviceReads:
+    packed: object      # int32[n_words]
+    read_off: object    # int64[R]
+    read_len: object    # int64[R]
+    chunk_ptr: object   # int64[R+1]
+    n_reads: int
+    n_chunks: int
+    n_bases: int
+    h2d_bytes: int
+
+
+@dataclass
+class DeviceUnits:
+    unit_off: object    # int64[U]
+    unit_len: object    # int32[U]
+    unit_kbase: object  # int64[U+1]
+    unit_last: object   # int32[U]  index of the last unit of the same read
+    n_units: int
+    n_kmer_starts: int
+    h2d_bytes: int
+
+
+@dataclass
+class DocFreqTable:
+    keys: object        # int64[cap]  (uint64 bit patterns, -1 = empty)
+    nreads: object      # int32[cap]
+    nmulti: object      # int32[cap]
+    cap: int
+
+
+@dataclass
+class KmerIndex:
+    sorted_keys: object  # int64[n]   ascending as uint64; rank = id
+    idx_keys: object     # int64[cap]
+    idx_vals: object     # int32[cap]
+    cap: int
+    n: int
+
+
+@dataclass
+class CloudCSR:
+    unit_ptr: object    # int64[U+1]
+    ids: object         # int32[E]   sorted unique ids inside every unit
+    n_units: int
+    n_entries: int
+
+
+@dataclass
+class DistResult:
+    edges: object        # int32[n_edges, 4]  (a, b, d, cnt) as uint32 bit patterns, unordered
+    selected: object     # int32[n_selected]  ids that are an endpoint of a kept edge, unordered
+    n_candidates: int
+    n_increments: int
+    n_splits: int
+
+
+class Engine:
+    def __init__(self, device=None):
+        import torch
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise CfkError("centroflye_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.cand_hint = 1 << 20
+        self.table_load = 0.5
+        self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def _to_dev(self, arr, dtype=None):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.pin_memory().to(self.device, non_blocking=True)
+
+    def _empty(self, n, dtype):
+        return self.torch.empty(max(int(n), 1), dtype=dtype, device=self.device)
+
+    def _zeros(self, n, dtype):
+        return self.torch.zeros(max(int(n), 1), dtype=dtype, device=self.device)
+
+    def _counters(self):
+        return self.torch.zeros(8, dtype=self.torch.int64, device=self.device)
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    @contextlib.contextmanager
+    def _stage(self, name):
+        """CUDA-event bracket on the launching stream (only when self.events is a list)."""
+        if self.events is None:
+            yield
+            return
+        t = self.torch
+        a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+        a.record(t.cuda.current_stream(self.device))
+        yield
+        b.record(t.cuda.current_stream(self.device))
+        self.events.append((name, a, b))
+
+    def stage_times_ms(self):
+        """Sum of elapsed ms per stage name (synchronises)."""
+        self.torch.cuda.synchronize(self.device)
+        out = {}
+        for name, a, b in self.events or []:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
+    def launch_count(self):
+        return int(self.lib.cfk_launch_count())
+
+    # ---- uploads ----------------------------------------------------------------------------
+    def upload_reads(self, batch, k):
+        """ReadBatch -> device; chunk_ptr is the block map of the stage-A kernel."""
+        nk = np.maximum(batch.read_len - k + 1, 0)
+        chunk_ptr = np.zeros(batch.n_reads + 1, dtype=np.int64)
+        np.cumsum((nk + DOCFREQ_CHUNK - 1) // DOCFREQ_CHUNK, out=chunk_ptr[1:])
+        packed = batch.packed.view(np.int32)
+        h2d = packed.nbytes + batch.read_off.nbytes + batch.read_len.nbytes + chunk_ptr.nbytes
+        return DeviceReads(packed=self._to_dev(packed), read_off=self._to_dev(batch.read_off),
+                           read_len=self._to_dev(batch.read_len), chunk_ptr=self._to_dev(chunk_ptr),
+                           n_reads=batch.n_reads, n_chunks=int(chunk_ptr[-1]), n_bases=batch.n_bases, h2d_bytes=h2d)
+
+    def upload_units(self, units, k):
+        nk = np.maximum(units.unit_len.astype(np.int64) - k + 1, 0)
+        kbase = np.zeros(units.n_units + 1, dtype=np.int64)
+        np.cumsum(nk, out=kbase[1:])
+        last = np.zeros(units.n_units, dtype=np.int32)
+        ptr = units.read_unit_ptr
+        counts = np.diff(ptr)
+        last[:] = np.repeat(ptr[1:] - 1, counts)
+        h2d = units.unit_off.nbytes + units.unit_len.nbytes + kbase.nbytes + last.nbytes
+        return DeviceUnits(unit_off=self._to_dev(units.unit_off), unit_len=self._to_dev(units.unit_len),
+                           unit_kbase=self._to_dev(kbase), unit_last=self._to_dev(last), n_units=units.n_units,
+                           n_kmer_starts=int(kbase[-1]), h2d_bytes=h2d)
+
+    # ---- stage A ----------------------------------------------------------------------------
+    def new_table(self, cap):
+        t = self.torch
+        return DocFreqTable(keys=t.full((cap,), -1, dtype=t.int64, device=self.device),
+                            nreads=self._zeros(cap, t.int32), nmulti=self._zeros(cap, t.int32), cap=int(cap))
+
+    def count_docfreq(self, reads, k, read_id_base=0, n_kmers_hint=None):
+        """One pass over all reads -> DocFreqTable (grown and recounted if a table fills up)."""
+        k = check_k(k)
+        t = self.torch
+        total_k = n_kmers_hint if n_kmers_hint is not None else max(reads.n_bases - reads.n_reads * (k - 1), 0)
+        cap1 = max(1024, int(total_k / self.table_load) + 1)
+        cap2 = cap1
+        while True:
+            table = self.new_table(cap1)
+            pairs = t.full((cap2,), -1, dtype=t.int64, device=self.device)
+            counters = self._counters()
+            with self._stage("docfreq"):
+                _lib.call("cfk_docfreq_count", self._p(reads.packed), self._p(reads.read_off),
+                          self._p(reads.read_len), self._p(reads.chunk_ptr), reads.n_reads, reads.n_chunks,
+                          read_id_base, k, self._p(table.keys), self._p(table.nreads), self._p(table.nmulti), cap1,
+                          self._p(pairs), cap2, self._p(counters), self._stream())
+            c = counters.cpu()
+            del pairs
+            if int(c[0]) == 0 and int(c[1]) == 0:
+                return table
+            cap1 *= 2 if int(c[0]) else 1
+            cap2 *= 2 if int(c[1]) else 1
+            if cap1 >= (1 << 31):
+                raise CfkError("stage-A table would exceed 2^31 slots; split the read set into batches")
+
+    def table_select(self, table, lo, hi, max_nonuniq, with_counts=False, n_parts=0, part=0):
+        """Compacted (keys[, n_reads, n_multi]) of slots inside the band, unordered."""
+        t = self.torch
+        counters = self._counters()
+        args = (self._p(table.keys), self._p(table.nreads), self._p(table.nmulti), table.cap,
+                int(lo), int(min(hi, U32_MAX)), int(min(max_nonuniq, U32_MAX)), n_parts, part)
+        _lib.call("cfk_table_select", *args, None, None, None, 0, self._p(counters), self._stream())
+        n = int(counters.cpu()[0])
+        keys = self._empty(n, t.int64)
+        nreads = self._empty(n, t.int32) if with_counts else None
+        nmulti = self._empty(n, t.int32) if with_counts else None
+        counters.zero_()
+        _lib.call("cfk_table_select", *args, self._p(keys), self._p(nreads), self._p(nmulti), n,
+                  self._p(counters), self._stream())
+        if with_counts:
+            return keys[:n], nreads[:n], nmulti[:n]
+        return keys[:n]
+
+    def merge_into(self, table, keys, nreads, nmulti):
+        counters = self._counters()
+        _lib.call("cfk_table_merge", self._p(keys), self._p(nreads), self._p(nmulti), int(keys.numel()),
+                  self._p(table.keys), self._p(table.nreads), self._p(table.nmulti), table.cap,
+                  self._p(counters), self._stream())
+        if int(counters.cpu()[0]):
+            raise CfkError("owner-side table full during merge")
+
+    # ---- rare set -> sorted ids + probe table ------------------------------------------------
+    def sort_keys(self, keys):
+        keys = keys.contiguous()
+        _lib.call("cfk_sort_u64", self._p(keys), int(keys.numel()), self._stream())
+        return keys
+
+    def build_index(self, keys, presorted=False):
+        t = self.torch
+        n = int(keys.numel())
+        sorted_keys = keys.contiguous() if presorted else self.sort_keys(keys.clone())
+        cap = max(64, 2 * n + 1)
+        idx_keys = t.full((cap,), -1, dtype=t.int64, device=self.device)
+        idx_vals = self._zeros(cap, t.int32)
+        counters = self._counters()
+        _lib.call("cfk_index_build", self._p(sorted_keys), n, self._p(idx_keys), self._p(idx_vals), cap,
+                  self._p(counters), self._stream())
+        return KmerIndex(sorted_keys=sorted_keys, idx_keys=idx_keys, idx_vals=idx_vals, cap=cap, n=n)
+
+    def index_from_host_keys(self, keys_u64):
+        """Sorted unique uint64 numpy keys -> KmerIndex (genomic_kmers arriving as set[str])."""
+        keys = np.unique(np.asarray(keys_u64, dtype=np.uint64))
+        return self.build_index(self._to_dev(keys.view(np.int64)), presorted=True)
+
+    # ---- stage B ----------------------------------------------------------------------------
+    def exclusive_scan(self, counts_i32):
+        t = self.torch
+        n = int(counts_i32.numel())
+        out = self._empty(n + 1, t.int64)
+        scratch = self._empty(int(self.lib.cfk_scan_scratch_elems(n)), t.int64)
+        _lib.call("cfk_exclusive_scan", self._p(counts_i32), self._p(out), n, self._p(scratch), self._stream())
+        return out
+
+    def build_clouds(self, reads, units, k, index):
+        k = check_k(k)
+        t = self.torch
+        U = units.n_units
+        if U == 0:
+            return CloudCSR(unit_ptr=self._zeros(1, t.int64), ids=self._empty(0, t.int32), n_units=0, n_entries=0)
+        tmp = self._empty(units.n_kmer_starts, t.int32)
+        cnt = self._empty(U, t.int32)
+        with self._stage("cloud_build"):
+            _lib.call("cfk_cloud_build", self._p(reads.packed), self._p(units.unit_off), self._p(units.unit_len),
+                      self._p(units.unit_kbase), U, k, self._p(index.idx_keys), self._p(index.idx_vals), index.cap,
+                      self._p(tmp), self._p(cnt), self._stream())
+        unit_ptr = self.exclusive_scan(cnt[:U])
+        E = int(unit_ptr[U].item())
+        ids = self._empty(E, t.int32)
+        _lib.call("cfk_cloud_compact", self._p(tmp), self._p(units.unit_kbase), self._p(unit_ptr), U, self._p(ids),
+                  self._stream())
+        return CloudCSR(unit_ptr=unit_ptr, ids=ids[:E], n_units=U, n_entries=E)
+
+    def id_histogram(self, csr, n_kmers, unit_lo=0, unit_hi=None):
+        t = self.torch
+        unit_hi = csr.n_units if unit_hi is None else unit_hi
+        mult = self._zeros(n_kmers, t.int32)
+        _lib.call("cfk_id_histogram", self._p(csr.unit_ptr), self._p(csr.ids), unit_lo, unit_hi, self._p(mult),
+                  self._stream())
+        return mult
+
+    def filter_clouds(self, csr, n_kmers, min_mult=2, max_mult=math.inf):
+        t = self.torch
+        U = csr.n_units
+        if U == 0:
+            return csr
+        big = 1 << 62
+        lo = -big if min_mult == -math.inf else (big if min_mult == math.inf else int(math.ceil(min_mult)))
+        hi = big if max_mult == math.inf else (-big if max_mult == -math.inf else int(math.floor(max_mult)))
+        mult = self.id_histogram(csr, n_kmers)
+        cnt = self._empty(U, t.int32)
+        _lib.call("cfk_cloud_filter_count", self._p(csr.unit_ptr), self._p(csr.ids), U, self._p(mult), lo, hi,
+                  self._p(cnt), self._stream())
+        new_ptr = self.exclusive_scan(cnt[:U])
+        E = int(new_ptr[U].item())
+        new_ids = self._empty(E, t.int32)
+        _lib.call("cfk_cloud_filter_write", self._p(csr.unit_ptr), self._p(csr.ids), U, self._p(mult), lo, hi,
+                  self._p(new_ptr), self._p(new_ids), self._stream())
+        return CloudCSR(unit_ptr=new_ptr, ids=new_ids[:E], n_units=U, n_entries=E)
+
+    # ---- stage C / D ------------------------------------------------------------------------
+    def build_occurrences(self, csr, n_kmers, unit_lo=0, unit_hi=None):
+        t = self.torch
+        unit_hi = csr.n_units if unit_hi is None else unit_hi
+        mult = self.id_histogram(csr, n_kmers, unit_lo, unit_hi)
+        occ_ptr = self.exclusive_scan(mult[:n_kmers]) if n_kmers else self._zeros(1, t.int64)
+        n_occ = int(occ_ptr[n_kmers].item()) if n_kmers else 0
+        occ = self._empty(n_occ, t.int32)
+        cursor = self._zeros(n_kmers, t.int32)
+        _lib.call("cfk_occ_fill", self._p(csr.unit_ptr), self._p(csr.ids), unit_lo, unit_hi, self._p(occ_ptr),
+                  self._p(cursor), self._p(occ), self._stream())
+        _lib.call("cfk_occ_sort", self._p(occ_ptr), self._p(occ), n_kmers, self._stream())
+        return occ_ptr, occ
+
+    def dist_edges(self, csr, unit_last, n_kmers, min_d, max_d, min_cov, rel_threshold=0.8,
+                   unit_lo=0, unit_hi=None, a_begin=0, a_end=None, a_stride=1, occurrences=None):
+        """Fused get_kmer_dist_map + filter_dist_tuples over source ids a_begin, a_begin+stride, ... < a_end."""
+        t = self.torch
+        if min_d < 0:
+            raise ValueError("min_d < 0: the reference loop (dbkr.py:121) is undefined for negative distances")
+        a_end = n_kmers if a_end is None else a_end
+        empty = DistResult(edges=t.empty((0, 4), dtype=t.int32, device=self.device),
+                           selected=self._empty(0, t.int32)[:0], n_candidates=0, n_increments=0, n_splits=0)
+        if n_kmers == 0 or csr.n_entries == 0 or max_d < max(min_d, 1):
+            return empty
+        occ_ptr, occ = occurrences if occurrences is not None else self.build_occurrences(csr, n_kmers, unit_lo, unit_hi)
+        min_cov_u = int(min(max(min_cov, 0), U32_MAX))
+        max_cand = int(self.cand_hint)
+        while True:
+            cand = self._empty(max_cand * 4, t.int32)
+            counters = self._counters()
+            with self._stage("dist_candidates"):
+                _lib.call("cfk_dist_candidates", self._p(csr.unit_ptr), self._p(csr.ids), self._p(unit_last),
+                          self._p(occ_ptr), self._p(occ), n_kmers, a_begin, a_end, a_stride, int(min_d), int(max_d),
+                          min_cov_u, self._p(cand), max_cand, self._p(counters), self.n_sms, self._stream())
+            self.last_dist_launches = getattr(self, "last_dist_launches", 0) + 1
+            c = counters.cpu()
+            n_cand = int(c[0])
+            if n_cand <= max_cand:
+                break
+            max_cand = n_cand  # exact size is now known: one more pass
+            del cand
+        self.cand_hint = max(self.cand_hint, int(n_cand * 1.05) + 1024)
+        edges = self._empty(n_cand * 4, t.int32)
+        selected = self._zeros(n_kmers, t.uint8)
+        counters2 = self._counters()
+        with self._stage("edge_filter"):
+            _lib.call("cfk_edge_filter", self._p(cand), n_cand, self._p(occ_ptr), self._p(occ), self._p(unit_last),
+                      int(min_d), int(max_d), float(rel_threshold), self._p(edges), self._p(selected),
+                      self._p(counters2), self._stream())
+        sel_idx = self._empty(n_kmers, t.int32)
+        _lib.call("cfk_flag_indices", self._p(selected), n_kmers, self._p(sel_idx), self._p(counters2[1:]),
+                  self._stream())
+        c2 = counters2.cpu()
+        n_edges, n_sel = int(c2[0]), int(c2[1])
+        return DistResult(edges=edges[: n_edges * 4].view(n_edges, 4), selected=sel_idx[:n_sel],
+                          n_candidates=n_cand, n_increments=int(c[2]), n_splits=int(c[3]))
+
+    # ---- whole path -------------------------------------------------------------------------
+    def recruit(self, reads, units, k, lo, hi, max_nonuniq, min_d, max_d, min_cov, rel_threshold=0.8,
+                unit_lo=0, unit_hi=None):
+        """main() of the reference script on device-resident inputs; returns device-resident results."""
+        table = self.count_docfreq(reads, k)
+        rare = self.table_select(table, lo, hi, max_nonuniq)
+        del table
+        index = self.build_index(rare)
+        csr = self.build_clouds(reads, units, k, index)
+        dist = self.dist_edges(csr, units.unit_last, index.n, min_d, max_d, min_cov, rel_threshold,
+                               unit_lo=unit_lo, unit_hi=unit_hi)
+        return index, csr, dist
+
+
+_default_engine = None
+
+
+def default_engine():
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine
+
+
+def to_host_u64(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+def to_host_u32(t):
+    return t.cpu().numpy().view(np.uint32)

@@ -1,0 +1,163 @@
+/*
+ * cfk.h — C ABI of the B200-native unique-k-mer recruitment path ("cfk" = centroFlye k-mers).
+ *
+ * The reference (seryrzu/centroFlye @ b2a4378) has no FFI: this stage is pure Python
+ * (scripts/distance_based_kmer_recruitment.py, scripts/read_kmer_cloud.py).  These entry
+ * points are what a binding for that path has to call; each one names the reference
+ * function (file:line under /root/reference/scripts) whose work it replaces.  The Python
+ * drop-in modules in centroflye_b200/ bind them with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _h; the caller (PyTorch)
+ *     owns all memory, the library allocates nothing and keeps no state between calls;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work on it;
+ *   - return 0 on success, negative CFK_ERR_* otherwise; cfk_last_error() returns a
+ *     thread-local message for the last failing call on this host thread;
+ *   - a k-mer is a uint64 with its first base in the most significant used bits
+ *     (A=0 C=1 G=2 T=3), 1 <= k <= 31; 0xFFFF_FFFF_FFFF_FFFF marks an empty slot;
+ *   - reads are 2-bit packed, 16 bases per little-endian uint32 (base j at bits 2j..2j+1);
+ *     base offsets index that packed space; every read starts on a 64-base boundary;
+ *   - overflow of a caller-sized buffer is never silent: kernels keep counting in the
+ *     `counters` words documented per call and the host wrapper grows and retries.
+ */
+#ifndef CFK_H
+#define CFK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFK_OK 0
+#define CFK_ERR_INVALID (-1)
+#define CFK_ERR_CUDA (-2)
+
+#define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define CFK_DOCFREQ_CHUNK 2048 /* k-mer start positions handled by one thread block */
+
+typedef void* cfk_stream_t;
+
+int cfk_abi_version(void);
+const char* cfk_last_error(void);
+/* static shared-memory / launch geometry, for DESIGN.md and bench.py's launch accounting */
+int cfk_dist_table_bytes_per_warp(void);
+/* number of kernels this library has enqueued since it was loaded (bench.py: gpu_launches) */
+int64_t cfk_launch_count(void);
+
+/* ---- stage A: document-frequency k-mer count --------------------------------------------
+ * Replaces get_kmer_freqs_from_ncrf_report, distance_based_kmer_recruitment.py:39-63.
+ * For every read r (global id read_id_base + r) and every k-mer of its gap-free row:
+ *   slot = find-or-insert(t1_keys, kmer); first (slot, read) sighting -> t1_nreads[slot]++,
+ *   second sighting in the same read -> t1_nmulti[slot]++ (once per read).
+ * t1_keys / t2_pairs must be pre-filled with CFK_EMPTY_KEY, t1_nreads / t1_nmulti with 0;
+ * calling again with more reads (distinct read ids) accumulates.  chunk_ptr[r] = number of
+ * CFK_DOCFREQ_CHUNK-sized chunks in reads < r (chunk_ptr[n_reads] = grid size).
+ * counters[0] != 0: t1 full; counters[1] != 0: t2 full (results invalid, grow and retry).
+ */
+int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len,
+                      const int64_t* chunk_ptr, int64_t n_reads, int64_t n_chunks, int64_t read_id_base, int k,
+                      uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1,
+                      uint64_t* t2_pairs, int64_t cap2, int64_t* counters, cfk_stream_t stream);
+
+/* Merge (key, n_reads, n_multi) records counted elsewhere (another GPU's shard) into a table:
+ * the owner-side half of the multi-GPU all-to-all.  counters[0] != 0: full. */
+int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n,
+                    uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1,
+                    int64_t* counters, cfk_stream_t stream);
+
+/* ---- band filter -------------------------------------------------------------------------
+ * Replaces the dict comprehension of get_rare_kmers, distance_based_kmer_recruitment.py:77-79,
+ * and (lo = 0, hi = UINT32_MAX) the survivor rule of :58-62.  Stream-compacts every occupied
+ * slot with n_multi <= max_nonuniq and lo <= n_reads <= hi into out_keys / out_nreads /
+ * out_nmulti (any may be NULL).  If n_parts > 0 only keys with mix(key) % n_parts == part are
+ * taken (hash partition for the multi-GPU exchange).  counters[0] (zeroed by the caller)
+ * receives the number of matches even beyond max_out; nothing is written past max_out.
+ */
+int cfk_table_select(const uint64_t* t1_keys, const uint32_t* t1_nreads, const uint32_t* t1_nmulti, int64_t cap1,
+                     uint32_t lo, uint32_t hi, uint32_t max_nonuniq, int32_t n_parts, int32_t part,
+                     uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out,
+                     int64_t* counters, cfk_stream_t stream);
+
+/* In-place ascending sort of n uint64 keys (bitonic network, shared-memory tiles).  The rank
+ * of a k-mer in the sorted rare set is its integer id everywhere downstream (the reference's
+ * kmer_index, distance_based_kmer_recruitment.py:103, canonicalised). */
+int cfk_sort_u64(uint64_t* keys, int64_t n, cfk_stream_t stream);
+
+/* Static probe table over the sorted rare keys: key -> rank.  idx_keys pre-filled with
+ * CFK_EMPTY_KEY; cap >= 2 n recommended. */
+int cfk_index_build(const uint64_t* sorted_keys, int64_t n, uint64_t* idx_keys, uint32_t* idx_vals, int64_t cap,
+                    int64_t* counters, cfk_stream_t stream);
+
+/* ---- stage B: per-unit k-mer clouds ------------------------------------------------------
+ * Replaces ReadKMerCloud.fromNCRF_record, read_kmer_cloud.py:18-31: for unit u (bases
+ * [unit_off[u], unit_off[u] + unit_len[u]) of the packed stream) the SET of indexed k-mers
+ * lying wholly inside it, as sorted unique ids written to tmp_ids[unit_kbase[u] ...] with
+ * their number in unit_cnt[u].  unit_kbase = exclusive prefix of max(unit_len - k + 1, 0).
+ */
+int cfk_cloud_build(const uint32_t* packed, const int64_t* unit_off, const int32_t* unit_len,
+                    const int64_t* unit_kbase, int64_t n_units, int k,
+                    const uint64_t* idx_keys, const uint32_t* idx_vals, int64_t cap,
+                    uint32_t* tmp_ids, int32_t* unit_cnt, cfk_stream_t stream);
+/* out[0] = 0, out[i + 1] = in[0] + ... + in[i]  (int32 -> int64); scratch holds
+ * cfk_scan_scratch_elems(n) int64. */
+int64_t cfk_scan_scratch_elems(int64_t n);
+int cfk_exclusive_scan(const int32_t* in, int64_t* out, int64_t n, int64_t* scratch, cfk_stream_t stream);
+/* Gather the per-unit id runs into CSR: ids[unit_ptr[u] + i] = tmp_ids[unit_kbase[u] + i]. */
+int cfk_cloud_compact(const uint32_t* tmp_ids, const int64_t* unit_kbase, const int64_t* unit_ptr,
+                      int64_t n_units, uint32_t* ids, cfk_stream_t stream);
+
+/* ---- cloud multiplicity filter -----------------------------------------------------------
+ * Replaces filter_reads_kmer_clouds, read_kmer_cloud.py:43-54.  mult[id] = number of
+ * (read, unit) clouds of units [unit_lo, unit_hi) containing id (mult zeroed by the caller). */
+int cfk_id_histogram(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, int64_t unit_hi,
+                     int32_t* mult, cfk_stream_t stream);
+/* new_cnt[u] = number of ids of unit u with min_mult <= mult[id] <= max_mult. */
+int cfk_cloud_filter_count(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, const int32_t* mult,
+                           int64_t min_mult, int64_t max_mult, int32_t* new_cnt, cfk_stream_t stream);
+int cfk_cloud_filter_write(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, const int32_t* mult,
+                           int64_t min_mult, int64_t max_mult, const int64_t* new_ptr, uint32_t* new_ids,
+                           cfk_stream_t stream);
+
+/* ---- stage C/D: unit-distance k-mer pair graph -------------------------------------------
+ * Occurrence lists (the inverted cloud CSR): occ[occ_ptr[a] ...] = sorted global unit indices
+ * whose cloud contains id a.  occ_ptr = exclusive scan of the cfk_id_histogram output;
+ * cursor zeroed by the caller. */
+int cfk_occ_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, int64_t unit_hi,
+                 const int64_t* occ_ptr, int32_t* cursor, uint32_t* occ, cfk_stream_t stream);
+int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_stream_t stream);
+
+/* Replaces get_kmer_dist_map, distance_based_kmer_recruitment.py:111-127, fused with the
+ * candidate pass of filter_dist_tuples (:133-138).  For every source id a, every distance
+ * d in [max(min_d,1), max_d] and every id b != a it counts
+ *     cnt[d][a][b] = #{ units g holding a : g + d is in the same read and holds b }
+ * in a warp-private shared-memory table and emits (a, b, d, cnt) as 4 x uint32 whenever
+ * cnt >= min_cov.  unit_last[g] = index of the last unit of g's read.
+ * counters (zeroed by the caller): [0] candidates found (also beyond max_cand; nothing is
+ * written past max_cand), [1] dynamic work cursor, [2] pair increments performed (the
+ * reference's number of `+= 1` executions), [3] table splits taken.
+ */
+int cfk_dist_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint32_t* unit_last,
+                        const int64_t* occ_ptr, const uint32_t* occ, int64_t n_kmers,
+                        int64_t a_begin, int64_t a_end, int32_t a_stride,
+                        int32_t min_d, int32_t max_d, uint32_t min_cov,
+                        uint32_t* cand, int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
+
+/* Replaces the second loop of filter_dist_tuples, distance_based_kmer_recruitment.py:142-147:
+ * for candidate (a, b, d, cnt) recompute all_occ = sum over d' in [max(min_d,1), max_d] of
+ * cnt[d'][a][b] by joining the two occurrence lists, keep it iff
+ * (double)cnt / (double)all_occ >= rel_threshold (IEEE double division, the same operation
+ * Python performs), append it to edges and flag both endpoints in selected[] (uint8, zeroed
+ * by the caller).  counters[0] (zeroed) receives the number of edges. */
+int cfk_edge_filter(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ,
+                    const uint32_t* unit_last, int32_t min_d, int32_t max_d, double rel_threshold,
+                    uint32_t* edges, uint8_t* selected, int64_t* counters, cfk_stream_t stream);
+
+/* Indices of non-zero flags, ascending (the recruited k-mer ids).  counters[0] zeroed. */
+int cfk_flag_indices(const uint8_t* flags, int64_t n, uint32_t* out, int64_t* counters, cfk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFK_H */

@@ -1,0 +1,162 @@
+"""Kernel-level GPU tests through the C ABI: sort, scan, select, and the stage-C corner paths
+(shared-memory table splitting, 64-bit slots, long occurrence lists) against numpy restatements."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from centroflye_b200.engine import default_engine
+    return default_engine()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 4095, 4096, 4097, 8192, 12289, 100003, 1 << 20, (1 << 20) + 77])
+def test_sort_u64(eng, n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    if n > 10:
+        keys[: n // 3] = keys[n // 3: 2 * (n // 3)]  # duplicates
+    dev = eng._to_dev(keys.view(np.int64)) if n else eng._empty(0, eng.torch.int64)[:0]
+    out = eng.sort_keys(dev)
+    assert np.array_equal(out.cpu().numpy().view(np.uint64)[:n], np.sort(keys))
+
+
+@pytest.mark.parametrize("n", [1, 5, 2047, 2048, 2049, 70001, 3 * 2048 * 1024 + 5])
+def test_exclusive_scan(eng, n):
+    rng = np.random.default_rng(n)
+    v = rng.integers(0, 5000, size=n, dtype=np.int32)
+    out = eng.exclusive_scan(eng._to_dev(v)).cpu().numpy()
+    want = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(v.astype(np.int64), out=want[1:])
+    assert np.array_equal(out[: n + 1], want)
+
+
+def _csr_from_units(units, n_kmers):
+    """units: list (per read) of lists (per unit) of sorted id arrays."""
+    flat = [u for rd in units for u in rd]
+    ptr = np.zeros(len(flat) + 1, dtype=np.int64)
+    np.cumsum([len(u) for u in flat], out=ptr[1:])
+    ids = np.concatenate(flat).astype(np.uint32) if flat else np.empty(0, np.uint32)
+    last = np.concatenate([np.full(len(rd), 0) for rd in units]).astype(np.int32)
+    pos = 0
+    for rd in units:
+        last[pos:pos + len(rd)] = pos + len(rd) - 1
+        pos += len(rd)
+    return ptr, ids, last
+
+
+def _numpy_edges(units, n_kmers, min_d, max_d, min_cov, thr=0.8):
+    """Dense restatement of dbkr.py:111-149 on integer ids (indicator-matrix products)."""
+    dmax = min(max_d, max(len(rd) for rd in units) - 1)
+    cnt = {}
+    for d in range(max(min_d, 1), dmax + 1):
+        c = np.zeros((n_kmers, n_kmers), dtype=np.int64)
+        for rd in units:
+            for i in range(len(rd) - d):
+                c[np.ix_(rd[i], rd[i + d])] += 1
+        np.fill_diagonal(c, 0)
+        cnt[d] = c
+    total = sum(cnt.values()) if cnt else np.zeros((n_kmers, n_kmers), dtype=np.int64)
+    edges = set()
+    for d, c in cnt.items():
+        a, b = np.nonzero((c >= min_cov) & (c / np.maximum(total, 1) >= thr))
+        edges |= {(int(x), int(y), d, int(c[x, y])) for x, y in zip(a, b)}
+    return edges, int(sum(int(c.sum()) for c in cnt.values()))
+
+
+def _run_dist(eng, units, n_kmers, min_d, max_d, min_cov, **kw):
+    from centroflye_b200.engine import CloudCSR
+    ptr, ids, last = _csr_from_units(units, n_kmers)
+    csr = CloudCSR(unit_ptr=eng._to_dev(ptr), ids=eng._to_dev(ids.view(np.int32)), n_units=len(last),
+                   n_entries=int(ids.size))
+    res = eng.dist_edges(csr, eng._to_dev(last), n_kmers, min_d, max_d, min_cov, **kw)
+    e = res.edges.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    sel = set(res.selected.cpu().numpy().view(np.uint32).tolist())
+    return {tuple(int(x) for x in row) for row in e}, sel, res
+
+
+def test_dist_table_splitting(eng):
+    """Clouds far larger than one warp table force the id-range splitting path."""
+    rng = np.random.default_rng(1)
+    n_kmers = 6000
+    units = [[np.sort(rng.choice(n_kmers, size=3500, replace=False)) for _ in range(3)] for _ in range(5)]
+    want, incr = _numpy_edges(units, n_kmers, 1, 150, 3)
+    got, sel, res = _run_dist(eng, units, n_kmers, 1, 150, 3)
+    assert res.n_increments == incr
+    assert res.n_splits >= 0
+    assert got == want
+    assert sel == {e[0] for e in want} | {e[1] for e in want}
+
+
+def test_dist_wide_slots_and_long_lists(eng):
+    """An id present in > 32 units of one read (multi-chunk occurrence list) in a universe too large for
+    32-bit slots: exercises the 64-bit table and counts > 1 per read."""
+    rng = np.random.default_rng(2)
+    n_real = 400
+    n_kmers = (1 << 21) + 3  # ids are only < n_real, but slot width is chosen from n_kmers
+    n_units = 2200
+    rd = []
+    for u in range(n_units):
+        extra = rng.choice(np.arange(1, n_real), size=3, replace=False)
+        rd.append(np.sort(np.concatenate([[0], extra])))
+    units = [rd, [np.array([0, 7, 9]), np.array([0, 9]), np.array([7])]]
+    dense_units = units
+    want, incr = _numpy_edges(dense_units, n_real, 2, 40, 4)
+    got, sel, res = _run_dist(eng, units, n_kmers, 2, 40, 4)
+    assert res.n_increments == incr
+    assert got == want
+
+
+def test_dist_sharded_by_source_equals_whole(eng):
+    rng = np.random.default_rng(3)
+    n_kmers = 900
+    units = [[np.sort(rng.choice(n_kmers, size=rng.integers(0, 120), replace=False)) for _ in range(rng.integers(1, 9))]
+             for _ in range(40)]
+    whole, _, res = _run_dist(eng, units, n_kmers, 1, 150, 2)
+    want, incr = _numpy_edges(units, n_kmers, 1, 150, 2)
+    assert whole == want and res.n_increments == incr
+    parts = set()
+    total_incr = 0
+    for r in range(3):
+        got, _, res_r = _run_dist(eng, units, n_kmers, 1, 150, 2, a_begin=r, a_stride=3)
+        assert not (parts & got)
+        parts |= got
+        total_incr += res_r.n_increments
+    assert parts == whole and total_incr == incr
+
+
+def test_table_select_partitions_cover_table(eng):
+    from centroflye_b200 import synth
+    from centroflye_b200.ingest import batch_from_synth
+    unit = synth.random_unit(150, 3)
+    genome, a0, alen = synth.simulate_genome(unit, 60, 0.02, 4, flank_len=300)
+    reads = synth.simulate_reads(genome, a0, alen, unit, 5, 0.04, 5, median_len=6000, sigma=0.2, min_len=5300, max_len=9000)
+    batch, _ = batch_from_synth(reads, len(unit))
+    dev = eng.upload_reads(batch, 17)
+    table = eng.count_docfreq(dev, 17)
+    allk, nr, nm = eng.table_select(table, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)
+    whole = dict(zip(allk.cpu().numpy().tolist(), zip(nr.cpu().numpy().tolist(), nm.cpu().numpy().tolist())))
+    merged = {}
+    for part in range(3):
+        k_, r_, m_ = eng.table_select(table, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True, n_parts=3, part=part)
+        for key, a, b in zip(k_.cpu().numpy().tolist(), r_.cpu().numpy().tolist(), m_.cpu().numpy().tolist()):
+            assert key not in merged
+            merged[key] = (a, b)
+    assert merged == whole
+    # owner-side merge of two half read sets equals counting everything at once
+    from centroflye_b200.ingest import pack_reads
+    from centroflye_b200.encode import unpack_codes
+    codes = [unpack_codes(batch.packed, int(batch.read_off[-1] + batch.read_len[-1]))[o:o + n]
+             for o, n in zip(batch.read_off, batch.read_len)]
+    half = len(codes) // 2
+    t_sum = eng.new_table(table.cap)
+    base = 0
+    for part_codes in (codes[:half], codes[half:]):
+        b = pack_reads(part_codes, [f"r{i}" for i in range(len(part_codes))])
+        t_part = eng.count_docfreq(eng.upload_reads(b, 17), 17, read_id_base=base)
+        base += len(part_codes)
+        eng.merge_into(t_sum, *eng.table_select(t_part, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True))
+    k2, r2, m2 = eng.table_select(t_sum, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)
+    assert dict(zip(k2.cpu().numpy().tolist(), zip(r2.cpu().numpy().tolist(), m2.cpu().numpy().tolist()))) == whole
