@@ -160,7 +160,7 @@ def test_stage_edge_cases(mods, tmp_path):
     dbkr, rkc, NCRF_Report = mods
     from centroflye_b200 import synth
     unit = synth.random_unit(97, 11)
-    genome, a0, alen = synth.simulate_genome(unit, 80, 0.02, 5, flank_len=500)
+    genome, a0, alen = synth.simulate_genome(unit, 400, 0.02, 5, flank_len=500)
     reads = synth.simulate_reads(genome, a0, alen, unit, 6, 0.03, 6, median_len=6000, sigma=0.2, min_len=5300,
                                  max_len=9000)
     path = tmp_path / "r.ncrf"
@@ -199,13 +199,13 @@ def test_non_acgt_is_rejected_loudly(mods, tmp_path):
     dbkr, _, NCRF_Report = mods
     from centroflye_b200 import synth
     unit = synth.random_unit(97, 11)
-    genome, a0, alen = synth.simulate_genome(unit, 80, 0.02, 5, flank_len=500)
+    genome, a0, alen = synth.simulate_genome(unit, 400, 0.02, 5, flank_len=500)
     reads = synth.simulate_reads(genome, a0, alen, unit, 3, 0.03, 6, median_len=6000, sigma=0.2, min_len=5300,
                                  max_len=9000)
     path = tmp_path / "r.ncrf"
     synth.write_ncrf_report(path, reads, unit)
     text = open(path).read().split("\n")
-    i = next(i for i, ln in enumerate(text) if ln.startswith("read_"))
+    i = next(i for i, ln in enumerate(text) if ln.startswith("read_") and int(ln.split()[2][:-2]) >= 5000)
     head, row = text[i].rsplit(" ", 1)
     text[i] = head + " " + row[:100] + "N" + row[101:]
     open(path, "w").write("\n".join(text))
