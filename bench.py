@@ -209,7 +209,7 @@ def run_ours(args):
     if rank != 0:
         return
     peak, peak_src = peaks()
-    dc_ms = float(np.mean(stage_ms.get("dist_candidates", [0.0])))
+    dc_ms = float(np.mean(stage_ms.get("pair_candidates", [0.0])))
     n_incr = last.n_increments if runner is None else runner.last_increments
     alg_bytes = BYTES_PER_INCREMENT_C * n_incr
     achieved = alg_bytes / (dc_ms * 1e-3) / 1e9 if dc_ms > 0 else 0.0
@@ -221,10 +221,10 @@ def run_ours(args):
                                "6% errors, k=19, coverage=32, max_d=150: full recruitment + read_kmer_cloud build",
                    "scale": args.scale, "read_bases": int(n_bases_total), "reads": int(batch.n_reads),
                    "units": int(units.n_units), "pair_increments": int(n_incr),
-                   "candidates": int(last.n_candidates), "edges": int(last.edges.shape[0]),
+                   "candidates": int(last.n_candidates), "pair_candidates": int(last.n_pair_candidates), "edges": int(last.edges.shape[0]),
                    "unique_kmers": int(last.selected.numel()), "l2": "256 MiB flush write between timed steps",
                    "sharding": "replicas of the read set are NOT used: reads sharded by rank" if world > 1 else "single GPU"},
-        "roofline": {"kernel": "dist_candidates_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": "pair_candidates_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": peak_src, "kernel_ms": dc_ms,
                      "algorithmic_bytes": alg_bytes, "note": "32 B per pair increment (BASELINE.md §4); counting "

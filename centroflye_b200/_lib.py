@@ -18,7 +18,8 @@ _f64 = ctypes.c_double
 SIGNATURES = {
     "cfk_abi_version": (_int, []),
     "cfk_last_error": (ctypes.c_char_p, []),
-    "cfk_dist_table_bytes_per_warp": (_int, []),
+    "cfk_pair_table_bytes_per_warp": (_int, []),
+    "cfk_pair_warps_per_block": (_int, []),
     "cfk_launch_count": (_i64, []),
     "cfk_docfreq_count": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _i64, _p, _i64, _p, _p]),
     "cfk_table_merge": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p]),
@@ -34,8 +35,8 @@ SIGNATURES = {
     "cfk_cloud_filter_write": (_int, [_p, _p, _i64, _p, _i64, _i64, _p, _p, _p]),
     "cfk_occ_fill": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p]),
     "cfk_occ_sort": (_int, [_p, _p, _i64, _p]),
-    "cfk_dist_candidates": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p, _i32, _p]),
-    "cfk_edge_filter": (_int, [_p, _i64, _p, _p, _p, _i32, _i32, _f64, _p, _p, _p, _p]),
+    "cfk_pair_candidates": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p, _i32, _p]),
+    "cfk_pair_join": (_int, [_p, _i64, _p, _p, _p, _i32, _i32, _u32, _f64, _p, _i64, _p, _p, _p]),
     "cfk_flag_indices": (_int, [_p, _i64, _p, _p, _p]),
 }
 

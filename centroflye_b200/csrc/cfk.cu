@@ -571,157 +571,223 @@ __global__ void occ_sort_kernel(const int64_t* __restrict__ occ_ptr, uint32_t* o
 }
 
 // ============================================================================================
-// Stage C: pair counting.  One warp per source id a; for every distance d it merges the cloud
-// id lists of the units d after each occurrence of a into a warp-private shared-memory
-// table  slot = (b + 1) << cb | count  (count <= #occurrences, so cb = bits(m) suffices).
-// Lanes of one insert step hold ids of ONE sorted-unique list, i.e. distinct keys, so the
-// insert needs no atomics: claim by plain store, re-read after __syncwarp, loser moves on.
+// Stage C: pair candidates.  One warp per source id a.  The distances [dmin, dlim] are cut into
+// chunks [d0, d1]; for one chunk the warp streams, per occurrence g of a, the CONTIGUOUS id run
+// ids[unit_ptr[g+d0] .. unit_ptr[min(g+d1,last)+1]) into a warp-private shared-memory table
+//     slot = (b + 1) << cb | count            count = sum over d in the chunk of cnt[d][a][b]
+// and emits (a, b, d0, d1) for every b whose chunk total reaches min_cov -- a necessary
+// condition for any single cnt[d][a][b] >= min_cov.  Stage D resolves the exact per-distance
+// counts of those few pairs by joining the two occurrence lists.
+//
+// Insert protocol (no atomics): the lanes of one step hold DISTINCT keys (one sorted-unique
+// unit list, or a 32-run spanning unit boundaries de-duplicated with match.any), so a slot is
+// only ever updated by the single lane that holds its key; a lane claims an empty slot with
+// count 0 and re-reads it after __syncwarp() -- the loser of a claim race sees a foreign key and
+// probes on, the winner sees its own key and adds its increment.
+// Pruning (exact): cnt[d][a][b] >= min_cov needs >= min_cov occurrences g with g + d inside the
+// read, so distances beyond the min_cov-th largest remainder are never streamed.
 // ============================================================================================
-constexpr int DC_WARPS = 8;
-constexpr int DC_TBL_BYTES = 16384;
+constexpr int PC_WARPS = CFK_PAIR_WARPS;
+constexpr int PC_TBL_BYTES = CFK_PAIR_TABLE_BYTES;
 
-// inserts key b (if valid) into the warp's table; returns the number of NEW distinct keys (uniform)
 template <typename S>
-__device__ __forceinline__ int warp_insert(volatile S* tbl, uint32_t b, bool valid, int cb) {
-  constexpr int NS = DC_TBL_BYTES / (int)sizeof(S);
-  constexpr int LOG_NS = (NS == 4096) ? 12 : 11;
-  static_assert(NS == 4096 || NS == 2048, "table geometry");
+__device__ __forceinline__ int warp_insert(volatile S* tbl, uint32_t b, bool valid, uint32_t inc, int cb) {
+  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
+  constexpr int LOG_NS = (NS == 8192) ? 13 : (NS == 4096) ? 12 : (NS == 2048) ? 11 : 10;
+  static_assert(NS == 8192 || NS == 4096 || NS == 2048 || NS == 1024, "table geometry");
   const S key = (S)b + 1;
   uint32_t h = (b * 2654435761u) >> (32 - LOG_NS);
-  bool pending = valid;
-  int fresh = 0;
+  bool pending = valid, claimed = false;
   while (__any_sync(FULL, pending)) {
-    bool claimed = false;
     if (pending) {
-      S w = tbl[h];
-      if (w == 0) {
-        tbl[h] = (key << cb) | 1;
-        claimed = true;
-      } else if ((w >> cb) == key) {
-        tbl[h] = w + 1;
+      const S w = tbl[h];
+      if ((w >> cb) == key) {
+        tbl[h] = w + (S)inc;
         pending = false;
+      } else if (w == 0) {
+        tbl[h] = key << cb;  // claim with count 0; confirmed (or lost) by the next read
+        claimed = true;
       } else {
         h = (h + 1) & (NS - 1);
+        claimed = false;
       }
     }
     __syncwarp();
-    bool won = false;
-    if (claimed) {
-      S w = tbl[h];
-      if ((w >> cb) == key) { pending = false; won = true; }
-      else h = (h + 1) & (NS - 1);
-    }
-    fresh += __popc(__ballot_sync(FULL, won));
-    __syncwarp();
   }
-  return fresh;
+  return __popc(__ballot_sync(FULL, valid && claimed));  // keys that were new to the table
 }
 
-__device__ __forceinline__ int64_t lower_bound_ids(const uint32_t* __restrict__ ids, int64_t lo, int64_t hi, uint32_t v) {
+__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* __restrict__ v, int64_t lo, int64_t hi, int64_t x) {
   while (lo < hi) {
     int64_t mid = (lo + hi) >> 1;
-    if (__ldg(ids + mid) < v) lo = mid + 1; else hi = mid;
+    if ((int64_t)__ldg(v + mid) < x) lo = mid + 1; else hi = mid;
   }
   return lo;
 }
 
+struct PairArgs {
+  const int64_t* __restrict__ unit_ptr;
+  const uint32_t* __restrict__ ids;
+  const uint32_t* __restrict__ unit_last;
+  const uint32_t* __restrict__ occ_a;
+  int64_t m;
+  int64_t n_kmers;
+  uint32_t a;
+  uint32_t min_cov;
+  uint4* cand;
+  int64_t max_cand;
+  int64_t* counters;
+};
+
+// One table pass over distances [d0, d1] restricted to ids [lo_id, hi_id).  Returns the number
+// of distinct keys, or -1 if the table passed its maximum load (nothing emitted).
 template <typename S>
-__device__ void dist_one_distance(volatile S* tbl, const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
-                                  const uint32_t* __restrict__ unit_last, const uint32_t* __restrict__ occ_a, int64_t m,
-                                  uint32_t a, int d, int cb, int64_t n_kmers, uint32_t min_cov, uint4* cand,
-                                  int64_t max_cand, int64_t* counters, int64_t& incr_total, int64_t& splits) {
-  constexpr int NS = DC_TBL_BYTES / (int)sizeof(S);
+__device__ int pair_chunk_pass(volatile S* tbl, const PairArgs& A, int d0, int d1, int64_t lo_id, int64_t hi_id, int cb) {
+  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
   constexpr int MAXLOAD = NS * 3 / 4;
   const int lane = threadIdx.x & 31;
-  // how many list entries does this distance touch?
-  int64_t total = 0;
-  for (int64_t t0 = 0; t0 < m; t0 += 32) {
-    int64_t t = t0 + lane;
-    if (t < m) {
-      uint32_t g = __ldg(occ_a + t);
-      if ((int64_t)g + d <= (int64_t)__ldg(unit_last + g)) total += unit_ptr[g + d + 1] - unit_ptr[g + d];
+  const bool whole = (lo_id == 0 && hi_id >= A.n_kmers);
+  const bool multi = d1 > d0;  // runs may cross unit boundaries
+  {
+    uint4* clr = reinterpret_cast<uint4*>(const_cast<S*>(tbl));
+#pragma unroll 4
+    for (int i = lane; i < PC_TBL_BYTES / 16; i += 32) clr[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  int distinct = 0;
+  for (int64_t t0 = 0; t0 < A.m; t0 += 32) {
+    const int64_t t = t0 + lane;
+    int64_t beg = 0, end = 0, g = 0, hiu = -1;
+    if (t < A.m) {
+      g = (int64_t)__ldg(A.occ_a + t);
+      const int64_t last = (int64_t)__ldg(A.unit_last + g);
+      if (g + d0 <= last) {
+        hiu = min(g + (int64_t)d1, last);
+        beg = __ldg(A.unit_ptr + g + d0);
+        end = __ldg(A.unit_ptr + hiu + 1);
+        if (!whole && end > beg) {  // single unit (d0 == d1): cut the sorted list to the id range
+          const int64_t nb = lower_bound_u32(A.ids, beg, end, lo_id);
+          end = (hi_id >= A.n_kmers) ? end : lower_bound_u32(A.ids, nb, end, hi_id);
+          beg = nb;
+        }
+      }
+    }
+    unsigned segs = __ballot_sync(FULL, end > beg);
+    while (segs) {
+      const int src = __ffs(segs) - 1;
+      segs &= segs - 1;
+      const int64_t b0 = __shfl_sync(FULL, beg, src), e0 = __shfl_sync(FULL, end, src);
+      int64_t ub = -1;  // interior unit boundaries of this run, one per lane (d1 - d0 <= 31 of them)
+      if (multi) {
+        const int64_t gs = __shfl_sync(FULL, g, src), hs = __shfl_sync(FULL, hiu, src);
+        const int64_t u = gs + d0 + 1 + lane;
+        if (u <= hs) ub = __ldg(A.unit_ptr + u);
+      }
+      uint32_t nxt = (b0 + lane < e0) ? __ldg(A.ids + b0 + lane) : 0u;
+      for (int64_t p = b0; p < e0; p += 32) {
+        const uint32_t b = nxt;
+        const int64_t pe = min(p + 32, e0);
+        if (p + 32 + lane < e0) nxt = __ldg(A.ids + p + 32 + lane);  // next step's ids fly during the insert
+        bool valid = (p + lane < pe) && (b != A.a);
+        uint32_t inc = 1;
+        if (multi && __any_sync(FULL, ub > p && ub < pe)) {  // two units in one step: merge equal ids
+          const unsigned vm = __ballot_sync(FULL, valid);
+          const unsigned mm = __match_any_sync(FULL, b) & vm;
+          inc = (uint32_t)__popc(mm);
+          valid = valid && (lane == __ffs(mm) - 1);
+        }
+        distinct += warp_insert<S>(tbl, b, valid, inc, cb);
+        if (distinct > MAXLOAD) return -1;
+      }
     }
   }
-  for (int o = 16; o >= 1; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
-  if (total == 0) return;
-  int64_t width = n_kmers;
-  if (total > MAXLOAD) {
-    int64_t parts = (total + NS / 2 - 1) / (NS / 2);
-    width = max((int64_t)1, n_kmers / parts);
-  }
+  // emit (a, b, d0, d1) for every key whose chunk total reached min_cov
   const S cmask = ((S)1 << cb) - 1;
-  int64_t lo = 0;
-  while (lo < n_kmers) {
-    const int64_t hi = min(n_kmers, lo + width);
-    const bool whole = (lo == 0 && hi == n_kmers);
-    {
-      uint4* clr = reinterpret_cast<uint4*>(const_cast<S*>(tbl));
-      for (int i = lane; i < DC_TBL_BYTES / 16; i += 32) clr[i] = make_uint4(0, 0, 0, 0);
-    }
-    __syncwarp();
-    int distinct = 0;
-    int64_t incr = 0;
-    bool overflow = false;
-    for (int64_t t0 = 0; t0 < m && !overflow; t0 += 32) {
-      int64_t t = t0 + lane;
-      int64_t beg = 0, end = 0;
-      if (t < m) {
-        uint32_t g = __ldg(occ_a + t);
-        if ((int64_t)g + d <= (int64_t)__ldg(unit_last + g)) {
-          beg = unit_ptr[g + d];
-          end = unit_ptr[g + d + 1];
-          if (!whole && end > beg) {
-            int64_t nb = lower_bound_ids(ids, beg, end, (uint32_t)lo);
-            end = (hi >= n_kmers) ? end : lower_bound_ids(ids, nb, end, (uint32_t)hi);
-            beg = nb;
-          }
-        }
-      }
-      unsigned lists = __ballot_sync(FULL, end > beg);
-      while (lists && !overflow) {
-        const int src = __ffs(lists) - 1;
-        lists &= lists - 1;
-        const int64_t b0 = __shfl_sync(FULL, beg, src), e0 = __shfl_sync(FULL, end, src);
-        for (int64_t p = b0; p < e0; p += 32) {
-          const int64_t idx = p + lane;
-          bool valid = idx < e0;
-          uint32_t b = valid ? __ldg(ids + idx) : 0u;
-          valid = valid && (b != a);
-          incr += __popc(__ballot_sync(FULL, valid));
-          distinct += warp_insert<S>(tbl, b, valid, cb);
-          if (distinct > MAXLOAD) { overflow = true; break; }
-        }
+  constexpr int PER16 = 16 / (int)sizeof(S);
+  const uint4* rd = reinterpret_cast<const uint4*>(const_cast<const S*>(tbl));
+  for (int i = lane; i < PC_TBL_BYTES / 16; i += 32) {
+    const uint4 q = rd[i];
+    S w[PER16];
+    if constexpr (sizeof(S) == 4) { w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+    else { w[0] = ((uint64_t)q.y << 32) | q.x; w[1] = ((uint64_t)q.w << 32) | q.z; }
+    unsigned hit = 0;
+#pragma unroll
+    for (int j = 0; j < PER16; ++j) hit |= (w[j] != 0 && (uint32_t)(w[j] & cmask) >= A.min_cov) ? (1u << j) : 0u;
+    if (__any_sync(FULL, hit != 0)) {
+#pragma unroll
+      for (int j = 0; j < PER16; ++j) {
+        const bool take = (hit >> j) & 1u;
+        const int64_t pos = warp_append(take, A.counters);
+        if (take && pos < A.max_cand)
+          A.cand[pos] = make_uint4(A.a, (uint32_t)(w[j] >> cb) - 1u, (uint32_t)d0, (uint32_t)d1);
       }
     }
-    if (overflow && width > 1) {  // too many distinct ids for one table: halve the id range and redo it
-      width = max((int64_t)1, width >> 1);
-      ++splits;
-      continue;
+  }
+  __syncwarp();
+  return distinct;
+}
+
+template <typename S>
+__device__ void pair_source(volatile S* tbl, const PairArgs& A, int dmin, int dlim, int cb, float& ratio, int64_t& splits) {
+  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
+  constexpr int TARGET = NS / 2;  // planned number of distinct keys per pass
+  const int lane = threadIdx.x & 31;
+  const int64_t cnt_limit = (cb >= 32) ? (int64_t)0x7FFFFFFF : (((int64_t)1 << cb) - 1);
+  int d0 = dmin;
+  int nd_force = 31;
+  while (d0 <= dlim) {
+    // plan: lane l sums the id-run lengths of distances d0 .. d0 + l over all occurrences
+    int64_t tot = 0;
+    const int my_d1 = d0 + lane;
+    for (int64_t t = 0; t < A.m; ++t) {
+      const int64_t g = (int64_t)__ldg(A.occ_a + t);
+      const int64_t last = (int64_t)__ldg(A.unit_last + g);
+      if (g + d0 <= last) tot += __ldg(A.unit_ptr + min(g + (int64_t)my_d1, last) + 1) - __ldg(A.unit_ptr + g + d0);
     }
-    // emit (a, b, d, cnt) for every key that reached min_cov
-    for (int i = lane; i < NS; i += 32) {
-      S w = tbl[i];
-      uint32_t cnt = (uint32_t)(w & cmask);
-      bool take = (w != 0) && cnt >= min_cov;
-      int64_t pos = warp_append(take, counters);
-      if (take && pos < max_cand) cand[pos] = make_uint4(a, (uint32_t)(w >> cb) - 1u, (uint32_t)d, cnt);
+    const int64_t cap = max((int64_t)64, (int64_t)((float)TARGET / ratio));
+    const bool ok = lane < nd_force && my_d1 <= dlim && tot <= cap && min(tot, A.m * (int64_t)(lane + 1)) <= cnt_limit;
+    const unsigned okm = __ballot_sync(FULL, ok);
+    int nd = __ffs(~okm) - 1;  // leading lanes that fit (tot is non-decreasing in the lane)
+    if (nd < 1) nd = 1;
+    const int64_t tot_nd = __shfl_sync(FULL, tot, nd - 1);
+    if (tot_nd == 0) { d0 += nd; nd_force = 31; continue; }
+    const int d1 = d0 + nd - 1;
+    int64_t width = A.n_kmers;
+    if (nd == 1 && tot_nd > cap) width = max((int64_t)1, A.n_kmers / ((tot_nd + cap - 1) / cap));
+    bool redo = false;
+    int64_t lo_id = 0;
+    while (lo_id < A.n_kmers) {
+      const int64_t hi_id = (width >= A.n_kmers) ? A.n_kmers : min(A.n_kmers, lo_id + width);
+      const int distinct = pair_chunk_pass<S>(tbl, A, d0, d1, lo_id, hi_id, cb);
+      if (distinct < 0) {  // too many distinct ids for one table
+        ++splits;
+        ratio = 1.0f;
+        if (nd > 1) { nd_force = nd >> 1; redo = true; break; }
+        width = max((int64_t)1, width >> 1);
+        continue;
+      }
+      if (width >= A.n_kmers) ratio = fminf(1.0f, fmaxf(0.05f, 1.15f * (float)distinct / (float)tot_nd));
+      lo_id = hi_id;
     }
-    incr_total += incr;
-    lo = hi;
+    if (redo) continue;
+    d0 += nd;
+    nd_force = 31;
   }
 }
 
-__global__ void __launch_bounds__(DC_WARPS * 32)
-dist_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
+__global__ void __launch_bounds__(PC_WARPS * 32)
+pair_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
                        const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
                        const uint32_t* __restrict__ occ, int64_t n_kmers, int64_t a_begin, int64_t a_end,
                        int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint4* cand,
                        int64_t max_cand, int64_t* counters) {
-  extern __shared__ __align__(16) unsigned char dc_smem[];
+  extern __shared__ __align__(16) unsigned char pc_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* my_tbl = dc_smem + (size_t)warp * DC_TBL_BYTES;
+  unsigned char* my_tbl = pc_smem + (size_t)warp * PC_TBL_BYTES;
   const int dmin = max(min_d, 1);
+  const int kb = 64 - __clzll((unsigned long long)n_kmers);  // bits of the largest key b + 1 = n_kmers
   int64_t incr_total = 0, splits = 0;
+  float ratio = 1.0f;
   for (;;) {
     unsigned long long item = 0;
     if (lane == 0) item = atomicAdd((unsigned long long*)(counters + 1), 1ull);
@@ -732,26 +798,56 @@ dist_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __r
     const int64_t o0 = occ_ptr[a], m = occ_ptr[a + 1] - o0;
     if (m == 0) continue;
     const uint32_t* occ_a = occ + o0;
-    int64_t maxrem = 0;
+    // the reference's number of `+= 1` executions for this source (dbkr.py:126), in closed form:
+    // every id of every unit g + d, d in [dmin, dmax], minus the occurrences of a itself in them
+    int64_t entries = 0, self = 0, maxrem = 0;
     for (int64_t t0 = 0; t0 < m; t0 += 32) {
-      int64_t t = t0 + lane;
+      const int64_t t = t0 + lane;
       if (t < m) {
-        uint32_t g = __ldg(occ_a + t);
-        maxrem = max(maxrem, (int64_t)__ldg(unit_last + g) - (int64_t)g);
+        const int64_t g = (int64_t)__ldg(occ_a + t);
+        const int64_t last = (int64_t)__ldg(unit_last + g);
+        const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, last);
+        if (lo <= hi) {
+          entries += __ldg(unit_ptr + hi + 1) - __ldg(unit_ptr + lo);
+          self += lower_bound_u32(occ_a, t + 1, m, hi + 1) - lower_bound_u32(occ_a, t + 1, m, lo);
+        }
+        maxrem = max(maxrem, last - g);
       }
     }
-    for (int o = 16; o >= 1; o >>= 1) maxrem = max(maxrem, __shfl_xor_sync(FULL, maxrem, o));
-    const int dmax = (int)min((int64_t)max_d, maxrem);
-    const int cb = 64 - __clzll((unsigned long long)m);  // counts never exceed m
-    const bool narrow = cb < 32 && ((uint64_t)n_kmers + 1) <= (1ull << (32 - cb));
-    for (int d = dmin; d <= dmax; ++d) {
-      if (narrow)
-        dist_one_distance<uint32_t>((volatile uint32_t*)my_tbl, unit_ptr, ids, unit_last, occ_a, m, a, d, cb,
-                                    n_kmers, min_cov, cand, max_cand, counters, incr_total, splits);
-      else
-        dist_one_distance<uint64_t>((volatile uint64_t*)my_tbl, unit_ptr, ids, unit_last, occ_a, m, a, d, 32,
-                                    n_kmers, min_cov, cand, max_cand, counters, incr_total, splits);
+    for (int o = 16; o >= 1; o >>= 1) {
+      entries += __shfl_xor_sync(FULL, entries, o);
+      self += __shfl_xor_sync(FULL, self, o);
+      maxrem = max(maxrem, __shfl_xor_sync(FULL, maxrem, o));
     }
+    incr_total += entries - self;
+    int dlim = (int)min((int64_t)max_d, maxrem);
+    if (min_cov > 1) {
+      if ((uint64_t)m < (uint64_t)min_cov) continue;
+      // largest d with at least min_cov occurrences whose read still has a unit g + d
+      int lo_d = dmin - 1, hi_d = dlim;  // invariant: count(lo_d) >= min_cov or lo_d == dmin - 1
+      while (lo_d < hi_d) {
+        const int mid = (lo_d + hi_d + 1) >> 1;
+        int64_t c = 0;
+        for (int64_t t0 = 0; t0 < m; t0 += 32) {
+          const int64_t t = t0 + lane;
+          bool ge = false;
+          if (t < m) {
+            const int64_t g = (int64_t)__ldg(occ_a + t);
+            ge = (int64_t)__ldg(unit_last + g) - g >= mid;
+          }
+          c += __popc(__ballot_sync(FULL, ge));
+        }
+        if (c >= (int64_t)min_cov) lo_d = mid; else hi_d = mid - 1;
+      }
+      dlim = lo_d;
+    }
+    if (dlim < dmin) continue;
+    PairArgs A{unit_ptr, ids, unit_last, occ_a, m, n_kmers, a, min_cov, cand, max_cand, counters};
+    const int mb = 64 - __clzll((unsigned long long)m);  // a single-distance count never exceeds m
+    if (kb + mb <= 32 && (32 - kb) >= 8)
+      pair_source<uint32_t>((volatile uint32_t*)my_tbl, A, dmin, dlim, 32 - kb, ratio, splits);
+    else
+      pair_source<uint64_t>((volatile uint64_t*)my_tbl, A, dmin, dlim, 32, ratio, splits);
   }
   if (lane == 0) {
     if (incr_total) atomicAdd((unsigned long long*)(counters + 2), (unsigned long long)incr_total);
@@ -760,40 +856,67 @@ dist_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __r
 }
 
 // ============================================================================================
-// Stage D: one thread per candidate; all_occ by joining the two sorted occurrence lists.
+// Stage D: one thread per pair candidate (a, b, d0, d1).  Joins the sorted occurrence lists of a
+// and b: all_occ = #{(g, g') : g' - g in [dmin, dmax], same read} (dbkr.py:143) and the exact
+// cnt[d][a][b] for the distances of the chunk; keeps (a, b, d, cnt) iff cnt >= min_cov and
+// (double)cnt / (double)all_occ >= rel_threshold (dbkr.py:136,145).
 // ============================================================================================
-__global__ void edge_filter_kernel(const uint4* __restrict__ cand, int64_t n_cand, const int64_t* __restrict__ occ_ptr,
-                                   const uint32_t* __restrict__ occ, const uint32_t* __restrict__ unit_last,
-                                   int32_t min_d, int32_t max_d, double rel_threshold, uint4* edges,
-                                   uint8_t* selected, int64_t* counters) {
+__global__ void pair_join_kernel(const uint4* __restrict__ cand, int64_t n_cand, const int64_t* __restrict__ occ_ptr,
+                                 const uint32_t* __restrict__ occ, const uint32_t* __restrict__ unit_last,
+                                 int32_t min_d, int32_t max_d, uint32_t min_cov, double rel_threshold, uint4* edges,
+                                 int64_t max_edges, uint8_t* selected, int64_t* counters) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool keep = false;
+  const int dmin = max(min_d, 1);
   uint4 c = make_uint4(0, 0, 0, 0);
+  uint32_t dmask = 0;  // distances d0 + j of the chunk at which the pair co-occurs
+  uint64_t all_occ = 0;
+  int64_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
   if (i < n_cand) {
     c = cand[i];
-    const int64_t a0 = occ_ptr[c.x], a1 = occ_ptr[c.x + 1];
-    const int64_t b0 = occ_ptr[c.y], b1 = occ_ptr[c.y + 1];
-    const int dmin = max(min_d, 1);
-    uint64_t all_occ = 0;
+    a0 = occ_ptr[c.x]; a1 = occ_ptr[c.x + 1];
+    b0 = occ_ptr[c.y]; b1 = occ_ptr[c.y + 1];
+    int64_t j = b0;
     for (int64_t t = a0; t < a1; ++t) {
       const int64_t g = __ldg(occ + t);
       const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, (int64_t)__ldg(unit_last + g));
       if (lo > hi) continue;
-      int64_t l = b0, r = b1;  // first occ(b) >= lo
-      while (l < r) { int64_t mid = (l + r) >> 1; if ((int64_t)__ldg(occ + mid) < lo) l = mid + 1; else r = mid; }
-      int64_t first = l;
-      r = b1;                  // first occ(b) > hi
-      while (l < r) { int64_t mid = (l + r) >> 1; if ((int64_t)__ldg(occ + mid) <= hi) l = mid + 1; else r = mid; }
-      all_occ += (uint64_t)(l - first);
+      while (j < b1 && (int64_t)__ldg(occ + j) < lo) ++j;
+      for (int64_t jj = j; jj < b1; ++jj) {
+        const int64_t d = (int64_t)__ldg(occ + jj) - g;
+        if (d > hi - g) break;
+        ++all_occ;
+        if (d >= (int64_t)c.z && d <= (int64_t)c.w) dmask |= 1u << (int)(d - c.z);
+      }
     }
-    keep = all_occ > 0 && ((double)c.w / (double)all_occ) >= rel_threshold;
   }
-  int64_t pos = warp_append(keep, counters);
-  if (keep) {
-    edges[pos] = c;
-    selected[c.x] = 1;
-    selected[c.y] = 1;
+  uint32_t n_cand_d = 0;
+  while (__any_sync(FULL, dmask != 0)) {
+    bool keep = false;
+    uint32_t d = 0, cnt = 0;
+    if (dmask) {
+      d = c.z + (uint32_t)(__ffs(dmask) - 1);
+      dmask &= dmask - 1;
+      int64_t j = b0;
+      for (int64_t t = a0; t < a1; ++t) {  // cnt[d][a][b]: occurrences g of a with g + d holding b inside the read
+        const int64_t g = __ldg(occ + t);
+        if (g + d > (int64_t)__ldg(unit_last + g)) continue;
+        while (j < b1 && (int64_t)__ldg(occ + j) < g + d) ++j;
+        if (j < b1 && (int64_t)__ldg(occ + j) == g + d) ++cnt;
+      }
+      if (cnt >= min_cov) {
+        ++n_cand_d;
+        keep = ((double)cnt / (double)all_occ) >= rel_threshold;
+      }
+    }
+    const int64_t pos = warp_append(keep, counters);
+    if (keep) {
+      if (pos < max_edges) edges[pos] = make_uint4(c.x, c.y, d, cnt);
+      selected[c.x] = 1;
+      selected[c.y] = 1;
+    }
   }
+  for (int o = 16; o >= 1; o >>= 1) n_cand_d += __shfl_xor_sync(FULL, n_cand_d, o);
+  if ((threadIdx.x & 31) == 0 && n_cand_d) atomicAdd((unsigned long long*)(counters + 2), (unsigned long long)n_cand_d);
 }
 
 __global__ void flag_indices_kernel(const uint8_t* __restrict__ flags, int64_t n, uint32_t* out, int64_t* counters) {
@@ -814,7 +937,8 @@ extern "C" {
 
 int cfk_abi_version(void) { return 1; }
 const char* cfk_last_error(void) { return g_err; }
-int cfk_dist_table_bytes_per_warp(void) { return DC_TBL_BYTES; }
+int cfk_pair_table_bytes_per_warp(void) { return PC_TBL_BYTES; }
+int cfk_pair_warps_per_block(void) { return PC_WARPS; }
 int64_t cfk_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len,
@@ -981,37 +1105,38 @@ int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_str
   return CFK_OK;
 }
 
-int cfk_dist_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint32_t* unit_last,
+int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint32_t* unit_last,
                         const int64_t* occ_ptr, const uint32_t* occ, int64_t n_kmers, int64_t a_begin, int64_t a_end,
                         int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint32_t* cand,
                         int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream) {
-  if (n_kmers < 0 || n_kmers >= (1ll << 32) - 1) return fail(CFK_ERR_INVALID, "cfk_dist_candidates: bad n_kmers");
-  if (min_d < 0) return fail(CFK_ERR_INVALID, "cfk_dist_candidates: min_d < 0 is not defined by the reference loop");
-  if (a_begin < 0 || a_end > n_kmers || a_stride < 1) return fail(CFK_ERR_INVALID, "cfk_dist_candidates: bad id range");
-  if (max_cand < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_dist_candidates: bad sizes");
+  if (n_kmers < 0 || n_kmers >= (1ll << 32) - 1) return fail(CFK_ERR_INVALID, "cfk_pair_candidates: bad n_kmers");
+  if (min_d < 0) return fail(CFK_ERR_INVALID, "cfk_pair_candidates: min_d < 0 is not defined by the reference loop");
+  if (a_begin < 0 || a_end > n_kmers || a_stride < 1) return fail(CFK_ERR_INVALID, "cfk_pair_candidates: bad id range");
+  if (max_cand < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_pair_candidates: bad sizes");
   if (a_begin >= a_end || max_d < (min_d > 1 ? min_d : 1)) return CFK_OK;
   static bool attr_done = false;
-  const int smem = DC_WARPS * DC_TBL_BYTES;
+  const int smem = PC_WARPS * PC_TBL_BYTES;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dist_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_dist_candidates: cudaFuncSetAttribute", e);
+    cudaError_t e = cudaFuncSetAttribute(pair_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_pair_candidates: cudaFuncSetAttribute", e);
     attr_done = true;
   }
-  dist_candidates_kernel<<<(unsigned)n_blocks, DC_WARPS * 32, smem, (cudaStream_t)stream>>>(
+  pair_candidates_kernel<<<(unsigned)n_blocks, PC_WARPS * 32, smem, (cudaStream_t)stream>>>(
       unit_ptr, ids, unit_last, occ_ptr, occ, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
       max_cand, counters);
-  CFK_CHECK_LAUNCH("dist_candidates_kernel", 1);
+  CFK_CHECK_LAUNCH("pair_candidates_kernel", 1);
   return CFK_OK;
 }
 
-int cfk_edge_filter(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ,
-                    const uint32_t* unit_last, int32_t min_d, int32_t max_d, double rel_threshold, uint32_t* edges,
-                    uint8_t* selected, int64_t* counters, cfk_stream_t stream) {
-  if (n_cand < 0) return fail(CFK_ERR_INVALID, "cfk_edge_filter: n_cand < 0");
+int cfk_pair_join(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ,
+                  const uint32_t* unit_last, int32_t min_d, int32_t max_d, uint32_t min_cov, double rel_threshold,
+                  uint32_t* edges, int64_t max_edges, uint8_t* selected, int64_t* counters, cfk_stream_t stream) {
+  if (n_cand < 0 || max_edges < 0) return fail(CFK_ERR_INVALID, "cfk_pair_join: bad sizes");
   if (n_cand == 0) return CFK_OK;
-  edge_filter_kernel<<<(unsigned)blocks_for(n_cand, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)cand, n_cand, occ_ptr, occ, unit_last, min_d, max_d, rel_threshold, (uint4*)edges, selected, counters);
-  CFK_CHECK_LAUNCH("edge_filter_kernel", 1);
+  pair_join_kernel<<<(unsigned)blocks_for(n_cand, 128), 128, 0, (cudaStream_t)stream>>>(
+      (const uint4*)cand, n_cand, occ_ptr, occ, unit_last, min_d, max_d, min_cov, rel_threshold, (uint4*)edges,
+      max_edges, selected, counters);
+  CFK_CHECK_LAUNCH("pair_join_kernel", 1);
   return CFK_OK;
 }
 

@@ -83,9 +83,10 @@ class CloudCSR:
 class DistResult:
     edges: object        # int32[n_edges, 4]  (a, b, d, cnt) as uint32 bit patterns, unordered
     selected: object     # int32[n_selected]  ids that are an endpoint of a kept edge, unordered
-    n_candidates: int
-    n_increments: int
+    n_candidates: int        # (a, b, d) with cnt >= min_cov (the reference's candidate dict, dbkr.py:133-138)
+    n_increments: int        # executions of `+= 1` at dbkr.py:126
     n_splits: int
+    n_pair_candidates: int = 0  # (a, b, distance chunk) records handed from stage C to stage D
 
 
 class Engine:
@@ -98,6 +99,7 @@ class Engine:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.cand_hint = 1 << 20
+        self.edge_hint = 1 << 20
         self.table_load = 0.5
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
 
@@ -339,11 +341,10 @@ class Engine:
         while True:
             cand = self._empty(max_cand * 4, t.int32)
             counters = self._counters()
-            with self._stage("dist_candidates"):
-                _lib.call("cfk_dist_candidates", self._p(csr.unit_ptr), self._p(csr.ids), self._p(unit_last),
+            with self._stage("pair_candidates"):
+                _lib.call("cfk_pair_candidates", self._p(csr.unit_ptr), self._p(csr.ids), self._p(unit_last),
                           self._p(occ_ptr), self._p(occ), n_kmers, a_begin, a_end, a_stride, int(min_d), int(max_d),
                           min_cov_u, self._p(cand), max_cand, self._p(counters), self.n_sms, self._stream())
-            self.last_dist_launches = getattr(self, "last_dist_launches", 0) + 1
             c = counters.cpu()
             n_cand = int(c[0])
             if n_cand <= max_cand:
@@ -351,20 +352,30 @@ class Engine:
             max_cand = n_cand  # exact size is now known: one more pass
             del cand
         self.cand_hint = max(self.cand_hint, int(n_cand * 1.05) + 1024)
-        edges = self._empty(n_cand * 4, t.int32)
         selected = self._zeros(n_kmers, t.uint8)
-        counters2 = self._counters()
-        with self._stage("edge_filter"):
-            _lib.call("cfk_edge_filter", self._p(cand), n_cand, self._p(occ_ptr), self._p(occ), self._p(unit_last),
-                      int(min_d), int(max_d), float(rel_threshold), self._p(edges), self._p(selected),
-                      self._p(counters2), self._stream())
+        max_edges = max(int(self.edge_hint), n_cand + 1024)
+        while True:
+            edges = self._empty(max_edges * 4, t.int32)
+            counters2 = self._counters()
+            with self._stage("pair_join"):
+                _lib.call("cfk_pair_join", self._p(cand), n_cand, self._p(occ_ptr), self._p(occ), self._p(unit_last),
+                          int(min_d), int(max_d), min_cov_u, float(rel_threshold), self._p(edges), max_edges,
+                          self._p(selected), self._p(counters2), self._stream())
+            c2 = counters2.cpu()
+            n_edges = int(c2[0])
+            if n_edges <= max_edges:
+                break
+            max_edges = n_edges
+            del edges
+        self.edge_hint = max(self.edge_hint, int(n_edges * 1.05) + 1024)
         sel_idx = self._empty(n_kmers, t.int32)
-        _lib.call("cfk_flag_indices", self._p(selected), n_kmers, self._p(sel_idx), self._p(counters2[1:]),
+        counters3 = self._counters()
+        _lib.call("cfk_flag_indices", self._p(selected), n_kmers, self._p(sel_idx), self._p(counters3),
                   self._stream())
-        c2 = counters2.cpu()
-        n_edges, n_sel = int(c2[0]), int(c2[1])
+        n_sel = int(counters3.cpu()[0])
         return DistResult(edges=edges[: n_edges * 4].view(n_edges, 4), selected=sel_idx[:n_sel],
-                          n_candidates=n_cand, n_increments=int(c[2]), n_splits=int(c[3]))
+                          n_candidates=int(c2[2]), n_pair_candidates=n_cand, n_increments=int(c[2]),
+                          n_splits=int(c[3]))
 
     # ---- whole path -------------------------------------------------------------------------
     def recruit(self, reads, units, k, lo, hi, max_nonuniq, min_d, max_d, min_cov, rel_threshold=0.8,

@@ -36,13 +36,16 @@ extern "C" {
 
 #define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define CFK_DOCFREQ_CHUNK 2048 /* k-mer start positions handled by one thread block */
+#define CFK_PAIR_WARPS 14         /* warps per block of the stage-C kernel (one block per SM) */
+#define CFK_PAIR_TABLE_BYTES 16384 /* shared-memory counting table of one warp */
 
 typedef void* cfk_stream_t;
 
 int cfk_abi_version(void);
 const char* cfk_last_error(void);
 /* static shared-memory / launch geometry, for DESIGN.md and bench.py's launch accounting */
-int cfk_dist_table_bytes_per_warp(void);
+int cfk_pair_table_bytes_per_warp(void);
+int cfk_pair_warps_per_block(void);
 /* number of kernels this library has enqueued since it was loaded (bench.py: gpu_launches) */
 int64_t cfk_launch_count(void);
 
@@ -128,31 +131,36 @@ int cfk_occ_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, 
                  const int64_t* occ_ptr, int32_t* cursor, uint32_t* occ, cfk_stream_t stream);
 int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_stream_t stream);
 
-/* Replaces get_kmer_dist_map, distance_based_kmer_recruitment.py:111-127, fused with the
- * candidate pass of filter_dist_tuples (:133-138).  For every source id a, every distance
- * d in [max(min_d,1), max_d] and every id b != a it counts
- *     cnt[d][a][b] = #{ units g holding a : g + d is in the same read and holds b }
- * in a warp-private shared-memory table and emits (a, b, d, cnt) as 4 x uint32 whenever
- * cnt >= min_cov.  unit_last[g] = index of the last unit of g's read.
+/* Replaces the counting loop of get_kmer_dist_map, distance_based_kmer_recruitment.py:111-127,
+ * fused with the candidate pass of filter_dist_tuples (:133-138).  The reference keeps one
+ * counter per (d, a, b); here every source id a (a_begin, a_begin + a_stride, ... < a_end) is
+ * handled by one warp that cuts the distances [max(min_d,1), max_d] into chunks [d0, d1]
+ * (d1 - d0 <= 30), sums  sum_{d in chunk} cnt[d][a][b]  in a shared-memory table and emits the
+ * pair candidate (a, b, d0, d1) as 4 x uint32 whenever that sum reaches min_cov -- a necessary
+ * condition for cnt[d][a][b] >= min_cov at some d of the chunk.  Every (a, b, d) belongs to
+ * exactly one emitted or rejected chunk, so cfk_pair_join sees each possible edge once.
+ * unit_last[g] = index of the last unit of g's read.
  * counters (zeroed by the caller): [0] candidates found (also beyond max_cand; nothing is
- * written past max_cand), [1] dynamic work cursor, [2] pair increments performed (the
- * reference's number of `+= 1` executions), [3] table splits taken.
+ * written past max_cand), [1] dynamic work cursor, [2] pair increments (the reference's number
+ * of `+= 1` executions at :126, in closed form), [3] table overflows that forced a smaller chunk.
  */
-int cfk_dist_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint32_t* unit_last,
+int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint32_t* unit_last,
                         const int64_t* occ_ptr, const uint32_t* occ, int64_t n_kmers,
                         int64_t a_begin, int64_t a_end, int32_t a_stride,
                         int32_t min_d, int32_t max_d, uint32_t min_cov,
                         uint32_t* cand, int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
 
-/* Replaces the second loop of filter_dist_tuples, distance_based_kmer_recruitment.py:142-147:
- * for candidate (a, b, d, cnt) recompute all_occ = sum over d' in [max(min_d,1), max_d] of
- * cnt[d'][a][b] by joining the two occurrence lists, keep it iff
- * (double)cnt / (double)all_occ >= rel_threshold (IEEE double division, the same operation
- * Python performs), append it to edges and flag both endpoints in selected[] (uint8, zeroed
- * by the caller).  counters[0] (zeroed) receives the number of edges. */
-int cfk_edge_filter(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ,
-                    const uint32_t* unit_last, int32_t min_d, int32_t max_d, double rel_threshold,
-                    uint32_t* edges, uint8_t* selected, int64_t* counters, cfk_stream_t stream);
+/* Replaces both loops of filter_dist_tuples, distance_based_kmer_recruitment.py:131-149, for
+ * the pair candidates: joins the occurrence lists of a and b to get the exact cnt[d][a][b] for
+ * every d in [d0, d1] and all_occ = sum over d' in [max(min_d,1), max_d] of cnt[d'][a][b];
+ * keeps (a, b, d, cnt) iff cnt >= min_cov and (double)cnt / (double)all_occ >= rel_threshold
+ * (IEEE double division, the operation Python performs at :145), appends it to edges and flags
+ * both endpoints in selected[] (uint8, zeroed by the caller).
+ * counters (zeroed): [0] edges found (also beyond max_edges; nothing is written past
+ * max_edges), [2] number of (a, b, d) with cnt >= min_cov (the reference's candidate dict). */
+int cfk_pair_join(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ,
+                  const uint32_t* unit_last, int32_t min_d, int32_t max_d, uint32_t min_cov, double rel_threshold,
+                  uint32_t* edges, int64_t max_edges, uint8_t* selected, int64_t* counters, cfk_stream_t stream);
 
 /* Indices of non-zero flags, ascending (the recruited k-mer ids).  counters[0] zeroed. */
 int cfk_flag_indices(const uint8_t* flags, int64_t n, uint32_t* out, int64_t* counters, cfk_stream_t stream);
