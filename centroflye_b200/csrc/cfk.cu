@@ -570,6 +570,14 @@ __global__ void occ_sort_kernel(const int64_t* __restrict__ occ_ptr, uint32_t* o
   }
 }
 
+__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* __restrict__ v, int64_t lo, int64_t hi, int64_t x) {
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)__ldg(v + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 // ============================================================================================
 // Stage C: pair candidates.  One warp per source id a.  The distances [dmin, dlim] are cut into
 // chunks [d0, d1]; for one chunk the warp streams, per occurrence g of a, the CONTIGUOUS id run
@@ -579,51 +587,18 @@ __global__ void occ_sort_kernel(const int64_t* __restrict__ occ_ptr, uint32_t* o
 // condition for any single cnt[d][a][b] >= min_cov.  Stage D resolves the exact per-distance
 // counts of those few pairs by joining the two occurrence lists.
 //
-// Insert protocol (no atomics): the lanes of one step hold DISTINCT keys (one sorted-unique
-// unit list, or a 32-run spanning unit boundaries de-duplicated with match.any), so a slot is
-// only ever updated by the single lane that holds its key; a lane claims an empty slot with
-// count 0 and re-reads it after __syncwarp() -- the loser of a claim race sees a foreign key and
-// probes on, the winner sees its own key and adds its increment.
+// Insert protocol (no atomics, no per-probe synchronisation): the lanes of one step hold
+// DISTINCT keys (one sorted-unique unit list, or a 32-run spanning unit boundaries de-duplicated
+// with match.any), so an occupied slot is only ever updated by the single lane that holds its
+// key.  A lane that finds an empty slot CLAIMS it speculatively, writing key and increment in
+// one store, and moves on; at the start of the next step (after one __syncwarp) it re-reads the
+// slot: if another lane's claim landed there instead, the loser re-inserts its key in a rare
+// replay round.  The table is kept at most half full so that probe chains stay short.
 // Pruning (exact): cnt[d][a][b] >= min_cov needs >= min_cov occurrences g with g + d inside the
 // read, so distances beyond the min_cov-th largest remainder are never streamed.
 // ============================================================================================
 constexpr int PC_WARPS = CFK_PAIR_WARPS;
 constexpr int PC_TBL_BYTES = CFK_PAIR_TABLE_BYTES;
-
-template <typename S>
-__device__ __forceinline__ int warp_insert(volatile S* tbl, uint32_t b, bool valid, uint32_t inc, int cb) {
-  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
-  constexpr int LOG_NS = (NS == 8192) ? 13 : (NS == 4096) ? 12 : (NS == 2048) ? 11 : 10;
-  static_assert(NS == 8192 || NS == 4096 || NS == 2048 || NS == 1024, "table geometry");
-  const S key = (S)b + 1;
-  uint32_t h = (b * 2654435761u) >> (32 - LOG_NS);
-  bool pending = valid, claimed = false;
-  while (__any_sync(FULL, pending)) {
-    if (pending) {
-      const S w = tbl[h];
-      if ((w >> cb) == key) {
-        tbl[h] = w + (S)inc;
-        pending = false;
-      } else if (w == 0) {
-        tbl[h] = key << cb;  // claim with count 0; confirmed (or lost) by the next read
-        claimed = true;
-      } else {
-        h = (h + 1) & (NS - 1);
-        claimed = false;
-      }
-    }
-    __syncwarp();
-  }
-  return __popc(__ballot_sync(FULL, valid && claimed));  // keys that were new to the table
-}
-
-__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* __restrict__ v, int64_t lo, int64_t hi, int64_t x) {
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if ((int64_t)__ldg(v + mid) < x) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
 
 struct PairArgs {
   const int64_t* __restrict__ unit_ptr;
@@ -639,12 +614,74 @@ struct PairArgs {
   int64_t* counters;
 };
 
+template <typename S>
+struct PairLane {  // a lane's not yet verified claim, carried from one step to the next
+  int vslot;       // slot index, -1 = none
+  S vword;         // what the claim wrote
+};
+
+// probe until the key is counted or an empty slot is claimed (per-lane loop, no votes inside)
+template <typename S>
+__device__ __forceinline__ void pair_probe(volatile S* tbl, PairLane<S>& L, S key, uint32_t h, bool valid, uint32_t inc, int cb) {
+  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
+  while (valid) {
+    const S w = tbl[h];
+    if ((w >> cb) == key) {
+      tbl[h] = w + (S)inc;
+      valid = false;
+    } else if (w == 0) {
+      const S nw = (key << cb) | (S)inc;
+      tbl[h] = nw;  // speculative claim, verified at the start of the next step
+      L.vslot = (int)h;
+      L.vword = nw;
+      valid = false;
+    } else {
+      h = (h + 1) & (NS - 1);
+    }
+  }
+}
+
+// Verify the claims of the previous step; a lane whose claim was overwritten by another lane's
+// claim of the same slot re-inserts its key (rare).  Returns the number of verified claims,
+// i.e. keys that are new to the table.
+template <typename S>
+__device__ __forceinline__ int pair_verify(volatile S* tbl, PairLane<S>& L, int cb) {
+  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
+  __syncwarp();
+  bool won = false, lost = false;
+  if (L.vslot >= 0) {
+    won = (tbl[L.vslot] == L.vword);
+    lost = !won;
+  }
+  int fresh = __popc(__ballot_sync(FULL, won));
+  while (__any_sync(FULL, lost)) {  // replay round: the losers hold distinct keys, nobody else inserts
+    const S key = L.vword >> cb;
+    const uint32_t inc = (uint32_t)(L.vword & (((S)1 << cb) - 1));
+    const uint32_t h = ((uint32_t)L.vslot + 1) & (NS - 1);
+    L.vslot = -1;
+    pair_probe<S>(tbl, L, key, h, lost, inc, cb);
+    __syncwarp();
+    won = false;
+    const bool again = lost && L.vslot >= 0;  // claimed a new slot: verify that one too
+    lost = false;
+    if (again) {
+      won = (tbl[L.vslot] == L.vword);
+      lost = !won;
+    }
+    fresh += __popc(__ballot_sync(FULL, won));
+  }
+  L.vslot = -1;
+  return fresh;
+}
+
 // One table pass over distances [d0, d1] restricted to ids [lo_id, hi_id).  Returns the number
 // of distinct keys, or -1 if the table passed its maximum load (nothing emitted).
 template <typename S>
 __device__ int pair_chunk_pass(volatile S* tbl, const PairArgs& A, int d0, int d1, int64_t lo_id, int64_t hi_id, int cb) {
   constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
-  constexpr int MAXLOAD = NS * 3 / 4;
+  constexpr int LOG_NS = (NS == 8192) ? 13 : (NS == 4096) ? 12 : (NS == 2048) ? 11 : 10;
+  static_assert(NS == 8192 || NS == 4096 || NS == 2048 || NS == 1024, "table geometry");
+  constexpr int MAXLOAD = NS / 2;
   const int lane = threadIdx.x & 31;
   const bool whole = (lo_id == 0 && hi_id >= A.n_kmers);
   const bool multi = d1 > d0;  // runs may cross unit boundaries
@@ -653,7 +690,9 @@ __device__ int pair_chunk_pass(volatile S* tbl, const PairArgs& A, int d0, int d
 #pragma unroll 4
     for (int i = lane; i < PC_TBL_BYTES / 16; i += 32) clr[i] = make_uint4(0, 0, 0, 0);
   }
-  __syncwarp();
+  PairLane<S> L;
+  L.vslot = -1;
+  L.vword = 0;
   int distinct = 0;
   for (int64_t t0 = 0; t0 < A.m; t0 += 32) {
     const int64_t t = t0 + lane;
@@ -677,7 +716,7 @@ __device__ int pair_chunk_pass(volatile S* tbl, const PairArgs& A, int d0, int d
       const int src = __ffs(segs) - 1;
       segs &= segs - 1;
       const int64_t b0 = __shfl_sync(FULL, beg, src), e0 = __shfl_sync(FULL, end, src);
-      int64_t ub = -1;  // interior unit boundaries of this run, one per lane (d1 - d0 <= 31 of them)
+      int64_t ub = -1;  // interior unit boundaries of this run, one per lane (d1 - d0 <= 30 of them)
       if (multi) {
         const int64_t gs = __shfl_sync(FULL, g, src), hs = __shfl_sync(FULL, hiu, src);
         const int64_t u = gs + d0 + 1 + lane;
@@ -696,11 +735,13 @@ __device__ int pair_chunk_pass(volatile S* tbl, const PairArgs& A, int d0, int d
           inc = (uint32_t)__popc(mm);
           valid = valid && (lane == __ffs(mm) - 1);
         }
-        distinct += warp_insert<S>(tbl, b, valid, inc, cb);
+        distinct += pair_verify<S>(tbl, L, cb);
         if (distinct > MAXLOAD) return -1;
+        pair_probe<S>(tbl, L, (S)b + 1, (b * 2654435761u) >> (32 - LOG_NS), valid, inc, cb);
       }
     }
   }
+  distinct += pair_verify<S>(tbl, L, cb);
   // emit (a, b, d0, d1) for every key whose chunk total reached min_cov
   const S cmask = ((S)1 << cb) - 1;
   constexpr int PER16 = 16 / (int)sizeof(S);
@@ -712,7 +753,7 @@ __device__ int pair_chunk_pass(volatile S* tbl, const PairArgs& A, int d0, int d
     else { w[0] = ((uint64_t)q.y << 32) | q.x; w[1] = ((uint64_t)q.w << 32) | q.z; }
     unsigned hit = 0;
 #pragma unroll
-    for (int j = 0; j < PER16; ++j) hit |= (w[j] != 0 && (uint32_t)(w[j] & cmask) >= A.min_cov) ? (1u << j) : 0u;
+    for (int j = 0; j < PER16; ++j) hit |= ((uint32_t)(w[j] & cmask) >= A.min_cov && w[j] != 0) ? (1u << j) : 0u;
     if (__any_sync(FULL, hit != 0)) {
 #pragma unroll
       for (int j = 0; j < PER16; ++j) {
@@ -730,7 +771,7 @@ __device__ int pair_chunk_pass(volatile S* tbl, const PairArgs& A, int d0, int d
 template <typename S>
 __device__ void pair_source(volatile S* tbl, const PairArgs& A, int dmin, int dlim, int cb, float& ratio, int64_t& splits) {
   constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
-  constexpr int TARGET = NS / 2;  // planned number of distinct keys per pass
+  constexpr int TARGET = NS * 3 / 10;  // planned number of distinct keys per pass (hard limit NS / 2)
   const int lane = threadIdx.x & 31;
   const int64_t cnt_limit = (cb >= 32) ? (int64_t)0x7FFFFFFF : (((int64_t)1 << cb) - 1);
   int d0 = dmin;
@@ -744,7 +785,8 @@ __device__ void pair_source(volatile S* tbl, const PairArgs& A, int dmin, int dl
       const int64_t last = (int64_t)__ldg(A.unit_last + g);
       if (g + d0 <= last) tot += __ldg(A.unit_ptr + min(g + (int64_t)my_d1, last) + 1) - __ldg(A.unit_ptr + g + d0);
     }
-    const int64_t cap = max((int64_t)64, (int64_t)((float)TARGET / ratio));
+    // distinct/entries of the previous pass predicts this one; farther distances repeat less, hence the margin
+    const int64_t cap = max((int64_t)64, (int64_t)((float)TARGET / fminf(1.0f, 1.25f * ratio)));
     const bool ok = lane < nd_force && my_d1 <= dlim && tot <= cap && min(tot, A.m * (int64_t)(lane + 1)) <= cnt_limit;
     const unsigned okm = __ballot_sync(FULL, ok);
     int nd = __ffs(~okm) - 1;  // leading lanes that fit (tot is non-decreasing in the lane)
@@ -766,7 +808,7 @@ __device__ void pair_source(volatile S* tbl, const PairArgs& A, int dmin, int dl
         width = max((int64_t)1, width >> 1);
         continue;
       }
-      if (width >= A.n_kmers) ratio = fminf(1.0f, fmaxf(0.05f, 1.15f * (float)distinct / (float)tot_nd));
+      if (width >= A.n_kmers) ratio = fminf(1.0f, fmaxf(0.05f, (float)distinct / (float)tot_nd));
       lo_id = hi_id;
     }
     if (redo) continue;
@@ -775,7 +817,7 @@ __device__ void pair_source(volatile S* tbl, const PairArgs& A, int dmin, int dl
   }
 }
 
-__global__ void __launch_bounds__(PC_WARPS * 32)
+__global__ void __launch_bounds__(PC_WARPS * 32, 1)
 pair_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
                        const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
                        const uint32_t* __restrict__ occ, int64_t n_kmers, int64_t a_begin, int64_t a_end,

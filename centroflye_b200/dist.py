@@ -1,0 +1,185 @@
+"""Recruitment sharded over the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+
+The reference is single-process; this is the partitioning of SURVEY.md §8e:
+
+  reads         sharded by record across ranks (every rank holds whole reads and their units)
+  stage A       local document-frequency table -> hash partition (cfk_table_part_*) -> all-to-all of
+                (key, n_reads, n_multi) records -> the owner sums them (cfk_table_merge), applies max_nonuniq
+                and the rare band, and the rare keys are all-gathered, so every rank holds the same sorted set
+                (n_reads and n_multi are sums over reads, dbkr.py:55-59, hence additive over read shards)
+  stage B       local: clouds of the rank's own units against the global rare set
+  stage C/D     the cloud CSR is all-gathered (units concatenated in rank order) and the SOURCE k-mer ids are
+                dealt round-robin: rank r handles a = r, r + G, ...  No counter ever crosses a rank boundary
+                because all of cnt[.][a][.] lives with a's owner; edges / endpoint flags are gathered at the end.
+
+The collectives are written against torch.distributed only (all_to_all_single, all_gather_into_tensor), so the
+exchange logic below runs unchanged on gloo/CPU tensors (tests/test_dist_gloo.py) and NCCL/CUDA tensors.
+"""
+import numpy as np
+
+U32_MAX = 0xFFFFFFFF
+_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
+
+
+# ---- host restatement of the device hash (tests, and host-side routing of small key lists) ------------------
+def mix64_np(x):
+    x = np.asarray(x, dtype=np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xff51afd7ed558ccd)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xc4ceb9fe1a85ec53)
+        x ^= x >> np.uint64(33)
+    return x
+
+
+def key_owner_np(keys, n_parts):
+    """owner(key) of cfk_table_select / cfk_table_part_* (csrc/cfk.cu key_owner)."""
+    return (mix64_np(np.asarray(keys, dtype=np.uint64) ^ _GOLDEN) % np.uint64(n_parts)).astype(np.int64)
+
+
+# ---- variable-size collectives on top of torch.distributed ---------------------------------------------------
+def exchange_counts(send_counts, group=None):
+    """send_counts[p] = records this rank sends to p  ->  recv_counts[p] = records p sends to this rank."""
+    import torch.distributed as dist
+    recv = send_counts.new_empty(send_counts.shape)
+    dist.all_to_all_single(recv, send_counts, group=group)
+    return recv
+
+
+def all_to_all_v(send, send_counts, recv_counts, group=None):
+    """Rows of `send` are grouped by destination (send_counts rows each); returns the rows received,
+    grouped by source.  Counts are python ints."""
+    import torch.distributed as dist
+    out = send.new_empty((int(sum(recv_counts)),) + tuple(send.shape[1:]))
+    dist.all_to_all_single(out, send.contiguous(), output_split_sizes=[int(c) for c in recv_counts],
+                           input_split_sizes=[int(c) for c in send_counts], group=group)
+    return out
+
+
+def all_gather_v(t, group=None):
+    """Concatenation over ranks (rank order) of a 1-d tensor whose length differs per rank -> (cat, counts)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+    counts = torch.empty(world, dtype=torch.int64, device=t.device)
+    dist.all_gather_into_tensor(counts, n, group=group)
+    counts = [int(c) for c in counts.cpu().tolist()]
+    width = max(max(counts), 1)
+    padded = t.new_zeros(width)
+    padded[: t.numel()] = t
+    gathered = t.new_empty(world * width)
+    dist.all_gather_into_tensor(gathered, padded, group=group)
+    parts = [gathered[r * width: r * width + c] for r, c in enumerate(counts)]
+    return torch.cat(parts) if parts else t.new_empty(0), counts
+
+
+def merge_cloud_shards(cnt_all, unit_counts, last_all):
+    """Per-rank (|cloud| per unit, index of the last unit of the read, local numbering) -> global numbering.
+
+    cnt_all / last_all are the rank-order concatenations; unit_counts[r] = units of rank r.  Returns
+    (unit_last_global, unit_base) with unit_base[r] = first global unit index of rank r."""
+    import torch
+    base = np.zeros(len(unit_counts) + 1, dtype=np.int64)
+    np.cumsum(np.asarray(unit_counts, dtype=np.int64), out=base[1:])
+    shift = torch.repeat_interleave(torch.as_tensor(base[:-1], device=last_all.device),
+                                    torch.as_tensor(np.asarray(unit_counts, dtype=np.int64), device=last_all.device))
+    return (last_all.to(torch.int64) + shift).to(torch.int32), base
+
+
+class ShardedRecruiter:
+    """Whole recruitment path over `world` GPUs; `batch` / `units` are THIS rank's reads (ingest.ReadBatch / UnitIndex)."""
+
+    def __init__(self, engine, batch, units, k, rank, world, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.eng, self.k, self.rank, self.world, self.group = engine, k, rank, world, group
+        self.batch, self.units = batch, units
+        self.reads = engine.upload_reads(batch, k)
+        self.dunits = engine.upload_units(units, k)
+        n = torch.tensor([batch.n_bases], dtype=torch.int64, device=engine.device)
+        dist.all_reduce(n, group=group)
+        self.n_bases_total = int(n.item())
+        self.last_increments = 0
+        self.bytes_exchanged = 0
+
+    # ---- stage A exchange ---------------------------------------------------------------------------------
+    def global_rare_keys(self, table, lo, hi, max_nonuniq):
+        """Local table -> sorted rare keys of the WHOLE read set (identical on every rank)."""
+        eng, t, W = self.eng, self.torch, self.world
+        counts = eng.part_count(table, W)
+        send_counts = counts.cpu().tolist()
+        keys, nreads, nmulti = eng.part_scatter(table, W, counts)
+        recv_counts = exchange_counts(counts, self.group).cpu().tolist()
+        rk = all_to_all_v(keys, send_counts, recv_counts, self.group)
+        rr = all_to_all_v(nreads, send_counts, recv_counts, self.group)
+        rm = all_to_all_v(nmulti, send_counts, recv_counts, self.group)
+        self.bytes_exchanged += 16 * int(sum(send_counts))
+        n_recv = int(rk.numel())
+        owned = eng.new_table(max(1024, int(n_recv / eng.table_load) + 1))
+        if n_recv:
+            eng.merge_into(owned, rk, rr, rm)
+        mine = eng.table_select(owned, lo, hi, max_nonuniq) if lo <= hi else eng._empty(0, t.int64)[:0]
+        allk, _ = all_gather_v(mine.contiguous(), self.group)
+        return eng.sort_keys(allk.clone()) if allk.numel() else allk
+
+    # ---- stage B exchange ---------------------------------------------------------------------------------
+    def global_clouds(self, csr):
+        """Local CloudCSR -> (global CloudCSR, global unit_last) with units concatenated in rank order."""
+        from .engine import CloudCSR
+        eng, t = self.eng, self.torch
+        U = csr.n_units
+        cnt = (csr.unit_ptr[1:U + 1] - csr.unit_ptr[:U]).to(t.int32) if U else eng._empty(0, t.int32)[:0]
+        cnt_all, unit_counts = all_gather_v(cnt.contiguous(), self.group)
+        last_all, _ = all_gather_v(self.dunits.unit_last[:U].contiguous(), self.group)
+        ids_all, _ = all_gather_v(csr.ids[: csr.n_entries].contiguous(), self.group)
+        self.bytes_exchanged += 8 * U + 4 * csr.n_entries
+        unit_last, _ = merge_cloud_shards(cnt_all, unit_counts, last_all)
+        n_units = int(cnt_all.numel())
+        unit_ptr = eng.exclusive_scan(cnt_all) if n_units else eng._zeros(1, t.int64)
+        return CloudCSR(unit_ptr=unit_ptr, ids=ids_all, n_units=n_units, n_entries=int(ids_all.numel())), unit_last
+
+    # ---- whole path ---------------------------------------------------------------------------------------
+    def step(self, lo, hi, max_nonuniq, min_d, max_d, min_cov, rel_threshold=0.8, gather=True):
+        """-> (index, local CloudCSR, DistResult); with gather=True every rank ends up with all edges / endpoints."""
+        from .engine import DistResult
+        eng, t = self.eng, self.torch
+        table = eng.count_docfreq(self.reads, self.k)
+        rare = self.global_rare_keys(table, lo, hi, max_nonuniq)
+        del table
+        index = eng.build_index(rare, presorted=True)
+        csr = eng.build_clouds(self.reads, self.dunits, self.k, index)
+        gcsr, unit_last = self.global_clouds(csr)
+        res = eng.dist_edges(gcsr, unit_last, index.n, min_d, max_d, min_cov, rel_threshold,
+                             a_begin=self.rank, a_stride=self.world)
+        stats = t.tensor([res.n_increments, res.n_candidates, res.n_pair_candidates, res.n_splits], dtype=t.int64,
+                         device=eng.device)
+        self.dist.all_reduce(stats, group=self.group)
+        self.last_increments = int(stats[0].item())
+        if not gather:
+            return index, csr, res
+        edges, _ = all_gather_v(res.edges.reshape(-1).contiguous(), self.group)
+        flags = eng._zeros(index.n, t.int32)
+        if res.selected.numel():
+            flags[res.selected.to(t.int64)] = 1
+        self.dist.all_reduce(flags, op=self.dist.ReduceOp.MAX, group=self.group)
+        selected = t.nonzero(flags[: index.n]).reshape(-1).to(t.int32)
+        s = stats.cpu().tolist()
+        out = DistResult(edges=edges.view(-1, 4), selected=selected, n_candidates=s[1], n_increments=s[0],
+                         n_splits=s[3], n_pair_candidates=s[2])
+        return index, csr, out
+
+    def e2e_step(self, lo, hi, max_nonuniq, min_d, max_d, min_cov):
+        """Pinned host buffers -> host results (rank 0 reads edges / endpoints, every rank its own clouds)."""
+        eng = self.eng
+        self.reads = eng.upload_reads(self.batch, self.k)
+        self.dunits = eng.upload_units(self.units, self.k)
+        index, csr, res = self.step(lo, hi, max_nonuniq, min_d, max_d, min_cov)
+        out = [csr.unit_ptr.cpu(), csr.ids.cpu()]
+        if self.rank == 0:
+            out += [res.selected.cpu(), res.edges.cpu(), index.sorted_keys.cpu()]
+        self.torch.cuda.synchronize()
+        d2h = sum(x.numel() * x.element_size() for x in out)
+        return self.reads.h2d_bytes + self.dunits.h2d_bytes, d2h

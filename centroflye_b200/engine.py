@@ -224,6 +224,23 @@ class Engine:
             return keys[:n], nreads[:n], nmulti[:n]
         return keys[:n]
 
+    def part_count(self, table, n_parts):
+        """int64[n_parts] (device): occupied slots per hash partition (owner = mix64(key ^ golden) % n_parts)."""
+        counts = self._zeros(n_parts, self.torch.int64)
+        _lib.call("cfk_table_part_count", self._p(table.keys), table.cap, n_parts, self._p(counts), self._stream())
+        return counts
+
+    def part_scatter(self, table, n_parts, counts):
+        """All occupied slots grouped by partition: (keys, n_reads, n_multi), partition p contiguous."""
+        t = self.torch
+        total = int(counts.sum().item())
+        cursors = (t.cumsum(counts, 0) - counts).contiguous()
+        keys, nreads, nmulti = self._empty(total, t.int64), self._empty(total, t.int32), self._empty(total, t.int32)
+        _lib.call("cfk_table_part_scatter", self._p(table.keys), self._p(table.nreads), self._p(table.nmulti),
+                  table.cap, n_parts, self._p(cursors), self._p(keys), self._p(nreads), self._p(nmulti),
+                  self._stream())
+        return keys[:total], nreads[:total], nmulti[:total]
+
     def merge_into(self, table, keys, nreads, nmulti):
         counters = self._counters()
         _lib.call("cfk_table_merge", self._p(keys), self._p(nreads), self._p(nmulti), int(keys.numel()),

@@ -36,8 +36,8 @@ extern "C" {
 
 #define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define CFK_DOCFREQ_CHUNK 2048 /* k-mer start positions handled by one thread block */
-#define CFK_PAIR_WARPS 14         /* warps per block of the stage-C kernel (one block per SM) */
-#define CFK_PAIR_TABLE_BYTES 16384 /* shared-memory counting table of one warp */
+#define CFK_PAIR_WARPS 28         /* warps per block of the stage-C kernel (one block per SM) */
+#define CFK_PAIR_TABLE_BYTES 8192 /* shared-memory counting table of one warp */
 
 typedef void* cfk_stream_t;
 
@@ -135,10 +135,10 @@ int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_str
  * fused with the candidate pass of filter_dist_tuples (:133-138).  The reference keeps one
  * counter per (d, a, b); here every source id a (a_begin, a_begin + a_stride, ... < a_end) is
  * handled by one warp that cuts the distances [max(min_d,1), max_d] into chunks [d0, d1]
- * (d1 - d0 <= 30), sums  sum_{d in chunk} cnt[d][a][b]  in a shared-memory table and emits the
- * pair candidate (a, b, d0, d1) as 4 x uint32 whenever that sum reaches min_cov -- a necessary
- * condition for cnt[d][a][b] >= min_cov at some d of the chunk.  Every (a, b, d) belongs to
- * exactly one emitted or rejected chunk, so cfk_pair_join sees each possible edge once.
+ * (d1 - d0 <= 30), sums  sum_{d in chunk} cnt[d][a][b]  in a warp-private shared-memory table and
+ * emits the pair candidate (a, b, d0, d1) as 4 x uint32 whenever that sum reaches min_cov -- a
+ * necessary condition for cnt[d][a][b] >= min_cov at some d of the chunk.  Every (a, b, d)
+ * belongs to exactly one emitted or rejected chunk, so cfk_pair_join sees each possible edge once.
  * unit_last[g] = index of the last unit of g's read.
  * counters (zeroed by the caller): [0] candidates found (also beyond max_cand; nothing is
  * written past max_cand), [1] dynamic work cursor, [2] pair increments (the reference's number

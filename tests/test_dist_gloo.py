@@ -1,0 +1,128 @@
+"""world_size-2 tests of the multi-GPU exchange logic (centroflye_b200/dist.py) on the gloo backend, CPU tensors.
+
+The device kernels cannot run here; what is checked is everything AROUND them: the variable-size all-to-all /
+all-gather helpers, the owner rule, the additivity of (n_reads, n_multi) over read shards, the global numbering
+of all-gathered cloud shards, and that dealing source k-mers round-robin partitions the edge set.  The per-shard
+counting itself is done by the CPU oracle (test infrastructure), in place of libcfk.so.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT  # noqa: F401  (puts the repo root on sys.path)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _dataset():
+    from centroflye_b200 import synth
+    from centroflye_b200.ingest import batch_from_synth
+    unit = synth.hor_unit(3, 50, 0.25, seed=3)
+    genome, a0, alen = synth.simulate_genome(unit, 90, 0.03, 4, flank_len=800)
+    reads = synth.simulate_reads(genome, a0, alen, unit, 14, 0.04, 5, median_len=6500, sigma=0.3, min_len=5200,
+                                 max_len=12000)
+    return unit, reads, batch_from_synth
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from centroflye_b200 import dist as cdist
+        from oracle import c_oracle
+
+        # --- helpers --------------------------------------------------------------------------------------
+        send_counts = torch.tensor([rank + 1 + p for p in range(world)], dtype=torch.int64)
+        recv_counts = cdist.exchange_counts(send_counts)
+        assert recv_counts.tolist() == [p + 1 + rank for p in range(world)]
+        send = torch.cat([torch.full((int(c),), 100 * rank + p, dtype=torch.int64) for p, c in enumerate(send_counts)])
+        got = cdist.all_to_all_v(send, send_counts.tolist(), recv_counts.tolist())
+        want = torch.cat([torch.full((int(c),), 100 * p + rank, dtype=torch.int64) for p, c in enumerate(recv_counts)])
+        assert torch.equal(got, want)
+        cat, counts = cdist.all_gather_v(torch.arange(3 * rank, dtype=torch.int32))  # rank 0 contributes nothing
+        assert counts == [3 * r for r in range(world)]
+        assert torch.equal(cat, torch.cat([torch.arange(3 * r, dtype=torch.int32) for r in range(world)]))
+
+        # --- sharded stage A == global stage A ---------------------------------------------------------------
+        unit, reads, batch_from_synth = _dataset()
+        k, lo, hi, max_nonuniq = 15, 3, 12, 2
+        whole_batch, whole_units = batch_from_synth(reads, len(unit))
+        my_batch, my_units = batch_from_synth(reads[rank::world], len(unit))
+        keys, nr, nm = c_oracle.docfreq(c_oracle.unpacked_codes(my_batch), my_batch, k)
+        owner = cdist.key_owner_np(keys, world)
+        order = np.argsort(owner, kind="stable")
+        send_counts = np.bincount(owner, minlength=world).astype(np.int64)
+        recv_counts = cdist.exchange_counts(torch.from_numpy(send_counts)).tolist()
+        rk = cdist.all_to_all_v(torch.from_numpy(keys[order].view(np.int64)), send_counts.tolist(), recv_counts).numpy()
+        rr = cdist.all_to_all_v(torch.from_numpy(nr[order].astype(np.int64)), send_counts.tolist(), recv_counts).numpy()
+        rm = cdist.all_to_all_v(torch.from_numpy(nm[order].astype(np.int64)), send_counts.tolist(), recv_counts).numpy()
+        assert (cdist.key_owner_np(rk.view(np.uint64), world) == rank).all()
+        uk, inv = np.unique(rk.view(np.uint64), return_inverse=True)
+        sum_r = np.bincount(inv, weights=rr, minlength=uk.size).astype(np.int64)
+        sum_m = np.bincount(inv, weights=rm, minlength=uk.size).astype(np.int64)
+        mine = uk[(sum_m <= max_nonuniq) & (sum_r >= lo) & (sum_r <= hi)]
+        rare_all, _ = cdist.all_gather_v(torch.from_numpy(mine.view(np.int64)))
+        rare = np.sort(rare_all.numpy().view(np.uint64))
+        gk, gr, gm = c_oracle.docfreq(c_oracle.unpacked_codes(whole_batch), whole_batch, k)
+        want_rare = gk[(gm <= max_nonuniq) & (gr >= lo) & (gr <= hi)]
+        assert rare.size > 50 and np.array_equal(rare, want_rare)
+
+        # --- all-gathered cloud shards + round-robin sources == whole graph ----------------------------------
+        ptr, ids = c_oracle.clouds(c_oracle.unpacked_codes(my_batch), my_units, k, rare)
+        cnt_all, unit_counts = cdist.all_gather_v(torch.from_numpy(np.diff(ptr).astype(np.int32)))
+        last_all, _ = cdist.all_gather_v(torch.from_numpy(c_oracle.unit_last_of(my_units)))
+        ids_all, _ = cdist.all_gather_v(torch.from_numpy(ids.view(np.int32)))
+        unit_last, base = cdist.merge_cloud_shards(cnt_all, unit_counts, last_all)
+        assert unit_counts[rank] == my_units.n_units and int(base[-1]) == sum(unit_counts)
+        gptr = np.zeros(cnt_all.numel() + 1, dtype=np.int64)
+        np.cumsum(cnt_all.numpy(), out=gptr[1:])
+        gids = np.ascontiguousarray(ids_all.numpy().view(np.uint32))
+        gl = np.ascontiguousarray(unit_last.numpy())
+        assert (gl >= np.arange(gl.size)).all() and gl[-1] == gl.size - 1
+        part = c_oracle.dist_edges(gptr, gids, gl, rare.size, 1, 150, 2)  # all sources, on the global numbering
+        e = part["edges"]
+        mine_e = e[e[:, 0] % world == rank]  # what this rank's a = rank, rank + G, ... pass would emit
+        flat, _ = cdist.all_gather_v(torch.from_numpy(np.ascontiguousarray(mine_e).view(np.int32).reshape(-1)))
+        got_e = flat.numpy().view(np.uint32).reshape(-1, 4)
+        # reference: the unsharded read set (unit numbering differs, edges do not depend on it)
+        wptr, wids = c_oracle.clouds(c_oracle.unpacked_codes(whole_batch), whole_units, k, want_rare)
+        whole = c_oracle.dist_edges(wptr, wids, c_oracle.unit_last_of(whole_units), want_rare.size, 1, 150, 2)
+        canon = lambda x: x[np.lexsort((x[:, 3], x[:, 2], x[:, 1], x[:, 0]))]  # noqa: E731
+        assert whole["edges"].shape[0] > 20
+        assert np.array_equal(canon(got_e), canon(whole["edges"]))
+        assert part["n_increments"] == whole["n_increments"]
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_exchange_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+def test_owner_rule_is_a_partition():
+    from centroflye_b200.dist import key_owner_np, mix64_np
+    rng = np.random.default_rng(0)
+    keys = rng.integers(0, 1 << 62, size=5000, dtype=np.uint64)
+    for parts in (1, 2, 3, 8):
+        o = key_owner_np(keys, parts)
+        assert o.min() >= 0 and o.max() < parts
+        if parts > 1:
+            assert np.bincount(o, minlength=parts).min() > 5000 / parts * 0.8
+    # murmur3 finaliser known answers (restated independently: python ints)
+    def mix(x):
+        m = (1 << 64) - 1
+        x ^= x >> 33; x = (x * 0xff51afd7ed558ccd) & m; x ^= x >> 33; x = (x * 0xc4ceb9fe1a85ec53) & m; x ^= x >> 33
+        return x
+    assert [int(v) for v in mix64_np(keys[:50])] == [mix(int(v)) for v in keys[:50]]

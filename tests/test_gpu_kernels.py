@@ -160,3 +160,28 @@ def test_table_select_partitions_cover_table(eng):
         eng.merge_into(t_sum, *eng.table_select(t_part, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True))
     k2, r2, m2 = eng.table_select(t_sum, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)
     assert dict(zip(k2.cpu().numpy().tolist(), zip(r2.cpu().numpy().tolist(), m2.cpu().numpy().tolist()))) == whole
+
+
+def test_table_partition_matches_owner_rule(eng):
+    from centroflye_b200.dist import key_owner_np
+    rng = np.random.default_rng(9)
+    keys = np.unique(rng.integers(0, 1 << 40, size=20000, dtype=np.uint64))
+    nr = rng.integers(1, 50, size=keys.size, dtype=np.uint32)
+    nm = rng.integers(0, 5, size=keys.size, dtype=np.uint32)
+    table = eng.new_table(3 * keys.size + 7)
+    eng.merge_into(table, eng._to_dev(keys.view(np.int64)), eng._to_dev(nr.view(np.int32)), eng._to_dev(nm.view(np.int32)))
+    for parts in (1, 3, 8):
+        counts = eng.part_count(table, parts)
+        k_, r_, m_ = eng.part_scatter(table, parts, counts)
+        counts = counts.cpu().numpy()
+        owner = key_owner_np(keys, parts)
+        assert np.array_equal(counts, np.bincount(owner, minlength=parts))
+        got_k = k_.cpu().numpy().view(np.uint64)
+        off = np.concatenate([[0], np.cumsum(counts)])
+        for p in range(parts):
+            seg = got_k[off[p]:off[p + 1]]
+            assert (key_owner_np(seg, parts) == p).all()
+        order = np.argsort(got_k)
+        assert np.array_equal(got_k[order], keys)
+        assert np.array_equal(r_.cpu().numpy().view(np.uint32)[order], nr)
+        assert np.array_equal(m_.cpu().numpy().view(np.uint32)[order], nm)
