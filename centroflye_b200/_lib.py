@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcfk.so")
+LIB_PATH = os.environ.get("CFK_LIBRARY") or os.path.join(_HERE, "libcfk.so")  # override: tuning experiments only
 
 _p = ctypes.c_void_p
 _i64 = ctypes.c_int64
@@ -24,6 +24,8 @@ SIGNATURES = {
     "cfk_docfreq_count": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _i64, _p, _i64, _p, _p]),
     "cfk_table_merge": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p]),
     "cfk_table_select": (_int, [_p, _p, _p, _i64, _u32, _u32, _u32, _i32, _i32, _p, _p, _p, _i64, _p, _p]),
+    "cfk_table_part_count": (_int, [_p, _i64, _i32, _p, _p]),
+    "cfk_table_part_scatter": (_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
     "cfk_sort_u64": (_int, [_p, _i64, _p]),
     "cfk_index_build": (_int, [_p, _i64, _p, _p, _i64, _p, _p]),
     "cfk_cloud_build": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _i64, _p, _p, _p]),
@@ -35,7 +37,9 @@ SIGNATURES = {
     "cfk_cloud_filter_write": (_int, [_p, _p, _i64, _p, _i64, _i64, _p, _p, _p]),
     "cfk_occ_fill": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p]),
     "cfk_occ_sort": (_int, [_p, _p, _i64, _p]),
-    "cfk_pair_candidates": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p, _i32, _p]),
+    "cfk_unit_splits": (_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
+    "cfk_pair_candidates": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p,
+                                   _i32, _p]),
     "cfk_pair_join": (_int, [_p, _i64, _p, _p, _p, _i32, _i32, _u32, _f64, _p, _i64, _p, _p, _p]),
     "cfk_flag_indices": (_int, [_p, _i64, _p, _p, _p]),
 }

@@ -208,6 +208,57 @@ __global__ void table_select_kernel(const uint64_t* __restrict__ t1_keys, const 
   }
 }
 
+// ---- hash partition of a table for the multi-GPU exchange --------------------------------------
+// owner(key) = mix64(key ^ golden) % n_parts -- the same rule table_select_kernel applies.
+__device__ __forceinline__ int32_t key_owner(uint64_t key, int32_t n_parts) {
+  return (int32_t)(mix64(key ^ 0x9E3779B97F4A7C15ull) % (uint64_t)n_parts);
+}
+
+constexpr int TP_MAX_PARTS = 64;
+
+__global__ void __launch_bounds__(256) table_part_count_kernel(const uint64_t* __restrict__ t1_keys, int64_t cap1,
+                                                              int32_t n_parts, int64_t* counts) {
+  __shared__ int s_cnt[TP_MAX_PARTS];
+  if (threadIdx.x < TP_MAX_PARTS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap1; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = t1_keys[i];
+    if (key != EMPTY) atomicAdd(&s_cnt[key_owner(key, n_parts)], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < n_parts && s_cnt[threadIdx.x])
+    atomicAdd((unsigned long long*)(counts + threadIdx.x), (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// cursors[p] starts at the first output index of partition p; records of one partition end up
+// contiguous (in arbitrary order), which is the send layout of the all-to-all.
+__global__ void __launch_bounds__(256) table_part_scatter_kernel(const uint64_t* __restrict__ t1_keys,
+                                                                const uint32_t* __restrict__ t1_nreads,
+                                                                const uint32_t* __restrict__ t1_nmulti, int64_t cap1,
+                                                                int32_t n_parts, int64_t* cursors, uint64_t* out_keys,
+                                                                uint32_t* out_nreads, uint32_t* out_nmulti) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_iter = (cap1 + (int64_t)gridDim.x * blockDim.x - 1) / ((int64_t)gridDim.x * blockDim.x);
+  for (int64_t it = 0; it < n_iter; ++it) {  // every lane runs every iteration (warp collectives below)
+    const int64_t i = (it * gridDim.x + blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
+    uint64_t key = EMPTY;
+    if (i < cap1) key = t1_keys[i];
+    const bool valid = key != EMPTY;
+    const int32_t p = valid ? key_owner(key, n_parts) : -1;
+    const unsigned peers = __match_any_sync(FULL, p);
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (valid && lane == leader) base = atomicAdd((unsigned long long*)(cursors + p), (unsigned long long)__popc(peers));
+    base = __shfl_sync(FULL, base, leader);
+    if (valid) {
+      const int64_t pos = (int64_t)base + __popc(peers & ((1u << lane) - 1));
+      out_keys[pos] = key;
+      out_nreads[pos] = t1_nreads[i];
+      out_nmulti[pos] = t1_nmulti[i];
+    }
+  }
+}
+
 // ============================================================================================
 // Bitonic sort of u64 keys ("flip / disperse" form: every compare-exchange is ascending, so
 // indices >= n behave as +inf padding without being stored).
@@ -578,6 +629,17 @@ __device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* __restrict__ 
   return lo;
 }
 
+// usplit[7 u + j - 1] = position of the first id >= (n_kmers * j) >> 3 in unit u's sorted list, j = 1..7:
+// lets stage C cut any unit list at octant boundaries of the id space without searching.
+__global__ void unit_split_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids, int64_t n_units,
+                                  int64_t n_kmers, uint32_t* usplit) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_units * 7) return;
+  const int64_t u = i / 7;
+  const int j = (int)(i % 7) + 1;
+  usplit[i] = (uint32_t)lower_bound_u32(ids, unit_ptr[u], unit_ptr[u + 1], (n_kmers * j) >> 3);
+}
+
 // ============================================================================================
 // Stage C: pair candidates.  One warp per source id a.  The distances [dmin, dlim] are cut into
 // chunks [d0, d1]; for one chunk the warp streams, per occurrence g of a, the CONTIGUOUS id run
@@ -599,168 +661,232 @@ __device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* __restrict__ 
 // ============================================================================================
 constexpr int PC_WARPS = CFK_PAIR_WARPS;
 constexpr int PC_TBL_BYTES = CFK_PAIR_TABLE_BYTES;
+constexpr uint32_t PC_NONE = 0xFFFFFFFFu;
 
 struct PairArgs {
   const int64_t* __restrict__ unit_ptr;
   const uint32_t* __restrict__ ids;
   const uint32_t* __restrict__ unit_last;
   const uint32_t* __restrict__ occ_a;
+  const uint32_t* __restrict__ usplit;  // [7 per unit] octant split positions, may be null
   int64_t m;
   int64_t n_kmers;
   uint32_t a;
-  uint32_t min_cov;
+  uint32_t min_cov;  // >= 1
   uint4* cand;
   int64_t max_cand;
   int64_t* counters;
 };
 
+// shared-memory accesses by 32-bit shared-space address (cheaper addressing than generic pointers,
+// and the "memory" clobber keeps the compiler from caching table words across the warp barrier)
+template <typename S> __device__ __forceinline__ S lds(uint32_t a);
+template <> __device__ __forceinline__ uint32_t lds<uint32_t>(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+template <> __device__ __forceinline__ uint64_t lds<uint64_t>(uint32_t a) {
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts(uint32_t a, uint64_t v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 template <typename S>
-struct PairLane {  // a lane's not yet verified claim, carried from one step to the next
-  int vslot;       // slot index, -1 = none
-  S vword;         // what the claim wrote
+struct PairLane {      // per-lane insert state carried from one step to the next
+  uint32_t vaddr[2];   // shared addresses of the not yet verified claims, PC_NONE = none
+  S vword[2];          // what the claims wrote
+  int claims;          // slots this lane has claimed in the current pass
 };
 
-// probe until the key is counted or an empty slot is claimed (per-lane loop, no votes inside)
+// One insert step: every lane counts up to two ids (all ids of a step are distinct).  Probes until
+// each key is counted or an empty slot is claimed; per-lane loop, no votes inside, the two
+// probe chains of a lane are independent (ILP).
 template <typename S>
-__device__ __forceinline__ void pair_probe(volatile S* tbl, PairLane<S>& L, S key, uint32_t h, bool valid, uint32_t inc, int cb) {
-  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
-  while (valid) {
-    const S w = tbl[h];
-    if ((w >> cb) == key) {
-      tbl[h] = w + (S)inc;
-      valid = false;
-    } else if (w == 0) {
-      const S nw = (key << cb) | (S)inc;
-      tbl[h] = nw;  // speculative claim, verified at the start of the next step
-      L.vslot = (int)h;
-      L.vword = nw;
-      valid = false;
-    } else {
-      h = (h + 1) & (NS - 1);
+__device__ __forceinline__ void pair_probe2(uint32_t tbase, PairLane<S>& L, S key0, uint32_t h0, bool v0, S key1,
+                                            uint32_t h1, bool v1, int cb) {
+  constexpr uint32_t NS = PC_TBL_BYTES / (uint32_t)sizeof(S);
+  while (v0 || v1) {
+    const uint32_t a0 = tbase + h0 * (uint32_t)sizeof(S), a1 = tbase + h1 * (uint32_t)sizeof(S);
+    S w0 = 0, w1 = 0;
+    if (v0) w0 = lds<S>(a0);
+    if (v1) w1 = lds<S>(a1);
+    if (v0) {
+      if ((w0 >> cb) == key0) {
+        sts(a0, (S)(w0 + 1));
+        v0 = false;
+      } else if (w0 == 0) {
+        const S nw = (key0 << cb) | (S)1;
+        sts(a0, nw);  // speculative claim, verified at the start of the next step
+        L.vaddr[0] = a0;
+        L.vword[0] = nw;
+        ++L.claims;
+        v0 = false;
+      } else {
+        h0 = (h0 + 1 == NS) ? 0u : h0 + 1;
+      }
+    }
+    if (v1) {
+      if ((w1 >> cb) == key1) {
+        sts(a1, (S)(w1 + 1));
+        v1 = false;
+      } else if (w1 == 0) {
+        const S nw = (key1 << cb) | (S)1;
+        sts(a1, nw);
+        L.vaddr[1] = a1;
+        L.vword[1] = nw;
+        ++L.claims;
+        v1 = false;
+      } else {
+        h1 = (h1 + 1 == NS) ? 0u : h1 + 1;
+      }
     }
   }
 }
 
-// Verify the claims of the previous step; a lane whose claim was overwritten by another lane's
-// claim of the same slot re-inserts its key (rare).  Returns the number of verified claims,
-// i.e. keys that are new to the table.
+// Verify the claims of the previous step; a lane whose claim was overwritten by another claim of
+// the same slot re-inserts its key (rare).
 template <typename S>
-__device__ __forceinline__ int pair_verify(volatile S* tbl, PairLane<S>& L, int cb) {
-  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
+__device__ __forceinline__ void pair_verify(uint32_t tbase, PairLane<S>& L, int cb) {
+  constexpr uint32_t NS = PC_TBL_BYTES / (uint32_t)sizeof(S);
   __syncwarp();
-  bool won = false, lost = false;
-  if (L.vslot >= 0) {
-    won = (tbl[L.vslot] == L.vword);
-    lost = !won;
-  }
-  int fresh = __popc(__ballot_sync(FULL, won));
-  while (__any_sync(FULL, lost)) {  // replay round: the losers hold distinct keys, nobody else inserts
-    const S key = L.vword >> cb;
-    const uint32_t inc = (uint32_t)(L.vword & (((S)1 << cb) - 1));
-    const uint32_t h = ((uint32_t)L.vslot + 1) & (NS - 1);
-    L.vslot = -1;
-    pair_probe<S>(tbl, L, key, h, lost, inc, cb);
+  bool lost0 = false, lost1 = false;
+  if (L.vaddr[0] != PC_NONE) lost0 = lds<S>(L.vaddr[0]) != L.vword[0];
+  if (L.vaddr[1] != PC_NONE) lost1 = lds<S>(L.vaddr[1]) != L.vword[1];
+  while (__any_sync(FULL, lost0 || lost1)) {  // replay round: the losers hold distinct keys, nobody else inserts
+    uint32_t h0 = (L.vaddr[0] - tbase) / (uint32_t)sizeof(S) + 1, h1 = (L.vaddr[1] - tbase) / (uint32_t)sizeof(S) + 1;
+    if (h0 >= NS) h0 = 0;
+    if (h1 >= NS) h1 = 0;
+    L.vaddr[0] = PC_NONE;
+    L.vaddr[1] = PC_NONE;
+    L.claims -= (int)lost0 + (int)lost1;
+    pair_probe2<S>(tbase, L, (S)(L.vword[0] >> cb), h0, lost0, (S)(L.vword[1] >> cb), h1, lost1, cb);
     __syncwarp();
-    won = false;
-    const bool again = lost && L.vslot >= 0;  // claimed a new slot: verify that one too
-    lost = false;
-    if (again) {
-      won = (tbl[L.vslot] == L.vword);
-      lost = !won;
-    }
-    fresh += __popc(__ballot_sync(FULL, won));
+    lost0 = lost0 && L.vaddr[0] != PC_NONE && lds<S>(L.vaddr[0]) != L.vword[0];
+    lost1 = lost1 && L.vaddr[1] != PC_NONE && lds<S>(L.vaddr[1]) != L.vword[1];
   }
-  L.vslot = -1;
-  return fresh;
+  L.vaddr[0] = PC_NONE;
+  L.vaddr[1] = PC_NONE;
 }
 
-// One table pass over distances [d0, d1] restricted to ids [lo_id, hi_id).  Returns the number
-// of distinct keys, or -1 if the table passed its maximum load (nothing emitted).
+// position of the first id >= octant boundary j (0..8) in unit u's sorted list
+__device__ __forceinline__ uint32_t split_pos(const PairArgs& A, int64_t u, int j) {
+  if (j <= 0) return (uint32_t)__ldg(A.unit_ptr + u);
+  if (j >= 8) return (uint32_t)__ldg(A.unit_ptr + u + 1);
+  return __ldg(A.usplit + u * 7 + (j - 1));
+}
+
+// One table pass over distances [d0, d1] restricted to ids [lo_id, hi_id) (j_lo / j_hi: the same
+// range as octant indices of the precomputed per-unit split table, or -1).  Returns the number of
+// distinct keys, or -1 if the table passed its maximum load (nothing emitted).
 template <typename S>
-__device__ int pair_chunk_pass(volatile S* tbl, const PairArgs& A, int d0, int d1, int64_t lo_id, int64_t hi_id, int cb) {
-  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
-  constexpr int LOG_NS = (NS == 8192) ? 13 : (NS == 4096) ? 12 : (NS == 2048) ? 11 : 10;
-  static_assert(NS == 8192 || NS == 4096 || NS == 2048 || NS == 1024, "table geometry");
-  constexpr int MAXLOAD = NS / 2;
+__device__ int pair_chunk_pass(uint32_t tbase, const PairArgs& A, int d0, int d1, int64_t lo_id, int64_t hi_id, int j_lo,
+                               int j_hi, int cb) {
+  constexpr uint32_t NS = PC_TBL_BYTES / (uint32_t)sizeof(S);
+  constexpr int MAXLOAD = (int)(NS / 2);
   const int lane = threadIdx.x & 31;
   const bool whole = (lo_id == 0 && hi_id >= A.n_kmers);
-  const bool multi = d1 > d0;  // runs may cross unit boundaries
-  {
-    uint4* clr = reinterpret_cast<uint4*>(const_cast<S*>(tbl));
 #pragma unroll 4
-    for (int i = lane; i < PC_TBL_BYTES / 16; i += 32) clr[i] = make_uint4(0, 0, 0, 0);
-  }
+  for (int i = lane; i < PC_TBL_BYTES / 16; i += 32) sts128(tbase + (uint32_t)i * 16u, make_uint4(0, 0, 0, 0));
   PairLane<S> L;
-  L.vslot = -1;
-  L.vword = 0;
-  int distinct = 0;
+  L.vaddr[0] = L.vaddr[1] = PC_NONE;
+  L.vword[0] = L.vword[1] = 0;
+  L.claims = 0;
   for (int64_t t0 = 0; t0 < A.m; t0 += 32) {
     const int64_t t = t0 + lane;
-    int64_t beg = 0, end = 0, g = 0, hiu = -1;
+    int64_t ua = 1, ub = 0;  // unit run [ua, ub] of this lane's occurrence
+    uint32_t cut_b = 0, cut_e = 0;
     if (t < A.m) {
-      g = (int64_t)__ldg(A.occ_a + t);
+      const int64_t g = (int64_t)__ldg(A.occ_a + t);
       const int64_t last = (int64_t)__ldg(A.unit_last + g);
       if (g + d0 <= last) {
-        hiu = min(g + (int64_t)d1, last);
-        beg = __ldg(A.unit_ptr + g + d0);
-        end = __ldg(A.unit_ptr + hiu + 1);
-        if (!whole && end > beg) {  // single unit (d0 == d1): cut the sorted list to the id range
-          const int64_t nb = lower_bound_u32(A.ids, beg, end, lo_id);
-          end = (hi_id >= A.n_kmers) ? end : lower_bound_u32(A.ids, nb, end, hi_id);
-          beg = nb;
+        ua = g + d0;
+        ub = min(g + (int64_t)d1, last);
+        if (!whole) {  // single unit (d0 == d1): cut its sorted list to the id range
+          if (j_lo >= 0 && A.usplit != nullptr) {
+            cut_b = split_pos(A, ua, j_lo);
+            cut_e = split_pos(A, ua, j_hi);
+          } else {
+            const int64_t b64 = __ldg(A.unit_ptr + ua), e64 = __ldg(A.unit_ptr + ua + 1);
+            const int64_t nb = lower_bound_u32(A.ids, b64, e64, lo_id);
+            cut_b = (uint32_t)nb;
+            cut_e = (uint32_t)((hi_id >= A.n_kmers) ? e64 : lower_bound_u32(A.ids, nb, e64, hi_id));
+          }
+          if (cut_e <= cut_b) { ua = 1; ub = 0; }
         }
       }
     }
-    unsigned segs = __ballot_sync(FULL, end > beg);
-    while (segs) {
-      const int src = __ffs(segs) - 1;
-      segs &= segs - 1;
-      const int64_t b0 = __shfl_sync(FULL, beg, src), e0 = __shfl_sync(FULL, end, src);
-      int64_t ub = -1;  // interior unit boundaries of this run, one per lane (d1 - d0 <= 30 of them)
-      if (multi) {
-        const int64_t gs = __shfl_sync(FULL, g, src), hs = __shfl_sync(FULL, hiu, src);
-        const int64_t u = gs + d0 + 1 + lane;
-        if (u <= hs) ub = __ldg(A.unit_ptr + u);
+    unsigned runs = __ballot_sync(FULL, ua <= ub);
+    while (runs) {
+      const int src = __ffs(runs) - 1;
+      runs &= runs - 1;
+      const int64_t us = __shfl_sync(FULL, ua, src);
+      const int nu = (int)(__shfl_sync(FULL, ub, src) - us) + 1;  // 1..31 units
+      // unit boundaries of the run, one per lane: unit j spans [bnd_j, bnd_{j+1})
+      uint32_t bnd = 0;
+      if (whole) {
+        if (lane <= nu) bnd = (uint32_t)__ldg(A.unit_ptr + us + lane);  // < 2^32 cloud entries (checked by the host)
+      } else {
+        const uint32_t cb0 = __shfl_sync(FULL, cut_b, src), ce0 = __shfl_sync(FULL, cut_e, src);
+        bnd = lane == 0 ? cb0 : ce0;
       }
-      uint32_t nxt = (b0 + lane < e0) ? __ldg(A.ids + b0 + lane) : 0u;
-      for (int64_t p = b0; p < e0; p += 32) {
-        const uint32_t b = nxt;
-        const int64_t pe = min(p + 32, e0);
-        if (p + 32 + lane < e0) nxt = __ldg(A.ids + p + 32 + lane);  // next step's ids fly during the insert
-        bool valid = (p + lane < pe) && (b != A.a);
-        uint32_t inc = 1;
-        if (multi && __any_sync(FULL, ub > p && ub < pe)) {  // two units in one step: merge equal ids
-          const unsigned vm = __ballot_sync(FULL, valid);
-          const unsigned mm = __match_any_sync(FULL, b) & vm;
-          inc = (uint32_t)__popc(mm);
-          valid = valid && (lane == __ffs(mm) - 1);
+      int j = 0;
+      uint32_t p = __shfl_sync(FULL, bnd, 0), e = __shfl_sync(FULL, bnd, 1);
+      while (p >= e && j + 1 < nu) { ++j; p = e; e = __shfl_sync(FULL, bnd, j + 1); }
+      if (p >= e) continue;
+      uint32_t b0 = (p + lane < e) ? __ldg(A.ids + p + lane) : A.a;
+      uint32_t b1 = (p + 32u + lane < e) ? __ldg(A.ids + p + 32u + lane) : A.a;
+      for (;;) {
+        // next window: the rest of this unit, else the next non-empty unit of the run
+        uint32_t np = p + 64u, ne = e;
+        int nj = j;
+        while (np >= ne && nj + 1 < nu) { ++nj; np = ne; ne = __shfl_sync(FULL, bnd, nj + 1); }
+        const bool more = np < ne;
+        uint32_t n0 = A.a, n1 = A.a;
+        if (more) {  // its ids fly during the insert of the current window
+          if (np + lane < ne) n0 = __ldg(A.ids + np + lane);
+          if (np + 32u + lane < ne) n1 = __ldg(A.ids + np + 32u + lane);
         }
-        distinct += pair_verify<S>(tbl, L, cb);
-        if (distinct > MAXLOAD) return -1;
-        pair_probe<S>(tbl, L, (S)b + 1, (b * 2654435761u) >> (32 - LOG_NS), valid, inc, cb);
+        pair_verify<S>(tbase, L, cb);
+        if (__reduce_add_sync(FULL, L.claims) > MAXLOAD) return -1;
+        // ids of one sorted-unique unit list are distinct; id a itself (also the filler of idle lanes) is skipped
+        pair_probe2<S>(tbase, L, (S)b0 + 1, __umulhi(b0 * 2654435761u, NS), b0 != A.a, (S)b1 + 1,
+                       __umulhi(b1 * 2654435761u, NS), b1 != A.a, cb);
+        if (!more) break;
+        p = np; e = ne; j = nj; b0 = n0; b1 = n1;
       }
     }
   }
-  distinct += pair_verify<S>(tbl, L, cb);
+  pair_verify<S>(tbase, L, cb);
+  const int distinct = __reduce_add_sync(FULL, L.claims);
   // emit (a, b, d0, d1) for every key whose chunk total reached min_cov
   const S cmask = ((S)1 << cb) - 1;
   constexpr int PER16 = 16 / (int)sizeof(S);
-  const uint4* rd = reinterpret_cast<const uint4*>(const_cast<const S*>(tbl));
   for (int i = lane; i < PC_TBL_BYTES / 16; i += 32) {
-    const uint4 q = rd[i];
+    const uint4 q = lds128(tbase + (uint32_t)i * 16u);
     S w[PER16];
     if constexpr (sizeof(S) == 4) { w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
     else { w[0] = ((uint64_t)q.y << 32) | q.x; w[1] = ((uint64_t)q.w << 32) | q.z; }
-    unsigned hit = 0;
+    uint32_t best = 0;
 #pragma unroll
-    for (int j = 0; j < PER16; ++j) hit |= ((uint32_t)(w[j] & cmask) >= A.min_cov && w[j] != 0) ? (1u << j) : 0u;
-    if (__any_sync(FULL, hit != 0)) {
+    for (int jj = 0; jj < PER16; ++jj) best = max(best, (uint32_t)(w[jj] & cmask));
+    if (__any_sync(FULL, best >= A.min_cov)) {  // rare
 #pragma unroll
-      for (int j = 0; j < PER16; ++j) {
-        const bool take = (hit >> j) & 1u;
+      for (int jj = 0; jj < PER16; ++jj) {
+        const bool take = (uint32_t)(w[jj] & cmask) >= A.min_cov;  // min_cov >= 1, so empty slots never pass
         const int64_t pos = warp_append(take, A.counters);
         if (take && pos < A.max_cand)
-          A.cand[pos] = make_uint4(A.a, (uint32_t)(w[j] >> cb) - 1u, (uint32_t)d0, (uint32_t)d1);
+          A.cand[pos] = make_uint4(A.a, (uint32_t)(w[jj] >> cb) - 1u, (uint32_t)d0, (uint32_t)d1);
       }
     }
   }
@@ -768,8 +894,13 @@ __device__ int pair_chunk_pass(volatile S* tbl, const PairArgs& A, int d0, int d
   return distinct;
 }
 
+__device__ __forceinline__ int64_t warp_sum_i64(int64_t v) {
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
 template <typename S>
-__device__ void pair_source(volatile S* tbl, const PairArgs& A, int dmin, int dlim, int cb, float& ratio, int64_t& splits) {
+__device__ void pair_source(uint32_t tbase, const PairArgs& A, int dmin, int dlim, int cb, float& ratio, int64_t& splits) {
   constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
   constexpr int TARGET = NS * 3 / 10;  // planned number of distinct keys per pass (hard limit NS / 2)
   const int lane = threadIdx.x & 31;
@@ -777,39 +908,71 @@ __device__ void pair_source(volatile S* tbl, const PairArgs& A, int dmin, int dl
   int d0 = dmin;
   int nd_force = 31;
   while (d0 <= dlim) {
-    // plan: lane l sums the id-run lengths of distances d0 .. d0 + l over all occurrences
-    int64_t tot = 0;
-    const int my_d1 = d0 + lane;
-    for (int64_t t = 0; t < A.m; ++t) {
-      const int64_t g = (int64_t)__ldg(A.occ_a + t);
-      const int64_t last = (int64_t)__ldg(A.unit_last + g);
-      if (g + d0 <= last) tot += __ldg(A.unit_ptr + min(g + (int64_t)my_d1, last) + 1) - __ldg(A.unit_ptr + g + d0);
-    }
     // distinct/entries of the previous pass predicts this one; farther distances repeat less, hence the margin
     const int64_t cap = max((int64_t)64, (int64_t)((float)TARGET / fminf(1.0f, 1.25f * ratio)));
-    const bool ok = lane < nd_force && my_d1 <= dlim && tot <= cap && min(tot, A.m * (int64_t)(lane + 1)) <= cnt_limit;
-    const unsigned okm = __ballot_sync(FULL, ok);
-    int nd = __ffs(~okm) - 1;  // leading lanes that fit (tot is non-decreasing in the lane)
-    if (nd < 1) nd = 1;
-    const int64_t tot_nd = __shfl_sync(FULL, tot, nd - 1);
-    if (tot_nd == 0) { d0 += nd; nd_force = 31; continue; }
+    // plan: extend the chunk one distance at a time (4 looked up per round) while its id runs fit
+    const int nd_max = min(nd_force, dlim - d0 + 1);
+    int nd = 0;
+    int64_t tot = 0, first = 0;
+    bool stop = false;
+    for (int jb = 0; jb < nd_max && !stop; jb += 4) {
+      int64_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      for (int64_t t0 = 0; t0 < A.m; t0 += 32) {
+        const int64_t t = t0 + lane;
+        if (t < A.m) {
+          const int64_t g = (int64_t)__ldg(A.occ_a + t);
+          const int64_t lim = (int64_t)__ldg(A.unit_last + g) + 1;
+          const int64_t u = g + d0 + jb;
+          const int64_t p0 = __ldg(A.unit_ptr + min(u, lim)), p1 = __ldg(A.unit_ptr + min(u + 1, lim)),
+                        p2 = __ldg(A.unit_ptr + min(u + 2, lim)), p3 = __ldg(A.unit_ptr + min(u + 3, lim)),
+                        p4 = __ldg(A.unit_ptr + min(u + 4, lim));
+          c0 += p1 - p0; c1 += p2 - p1; c2 += p3 - p2; c3 += p4 - p3;
+        }
+      }
+      const int64_t c[4] = {warp_sum_i64(c0), warp_sum_i64(c1), warp_sum_i64(c2), warp_sum_i64(c3)};
+      if (jb == 0) first = c[0];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (stop || jb + k >= nd_max) { stop = true; continue; }
+        const int64_t nt = tot + c[k];
+        if (nt <= cap && min(nt, A.m * (int64_t)(jb + k + 1)) <= cnt_limit) { tot = nt; ++nd; } else stop = true;
+      }
+    }
+    if (nd < 1) { nd = 1; tot = first; }
+    if (tot == 0) { d0 += nd; nd_force = 31; continue; }
     const int d1 = d0 + nd - 1;
-    int64_t width = A.n_kmers;
-    if (nd == 1 && tot_nd > cap) width = max((int64_t)1, A.n_kmers / ((tot_nd + cap - 1) / cap));
+    // A single distance too large for one table is cut by id range.  Octants of the id space have
+    // precomputed split positions in every unit list (usplit); finer cuts use binary search.
+    int64_t parts = 1;
+    if (nd == 1 && tot > cap) parts = (tot + cap - 1) / cap;
+    int pw = (parts <= 1) ? 8 : (parts <= 2) ? 4 : (parts <= 4) ? 2 : (parts <= 8) ? 1 : 0;  // octants per pass, 0 = free widths
+    int64_t width = (pw > 0) ? 0 : max((int64_t)1, A.n_kmers / parts);
     bool redo = false;
     int64_t lo_id = 0;
+    int jl = 0;
     while (lo_id < A.n_kmers) {
-      const int64_t hi_id = (width >= A.n_kmers) ? A.n_kmers : min(A.n_kmers, lo_id + width);
-      const int distinct = pair_chunk_pass<S>(tbl, A, d0, d1, lo_id, hi_id, cb);
-      if (distinct < 0) {  // too many distinct ids for one table
+      int64_t hi_id;
+      int j_lo = -1, j_hi = -1;
+      if (pw > 0) {
+        j_lo = jl;
+        j_hi = min(8, jl + pw);
+        hi_id = (j_hi == 8) ? A.n_kmers : (A.n_kmers * j_hi) >> 3;
+      } else {
+        hi_id = min(A.n_kmers, lo_id + width);
+      }
+      const int distinct = (hi_id > lo_id) ? pair_chunk_pass<S>(tbase, A, d0, d1, lo_id, hi_id, j_lo, j_hi, cb) : 0;
+      if (distinct < 0) {  // too many distinct ids for one table: smaller chunk, then smaller id ranges
         ++splits;
         ratio = 1.0f;
         if (nd > 1) { nd_force = nd >> 1; redo = true; break; }
+        if (pw > 1) { pw >>= 1; continue; }
+        if (pw == 1) { pw = 0; width = max((int64_t)1, (hi_id - lo_id) >> 1); continue; }
         width = max((int64_t)1, width >> 1);
         continue;
       }
-      if (width >= A.n_kmers) ratio = fminf(1.0f, fmaxf(0.05f, (float)distinct / (float)tot_nd));
+      if (pw == 8) ratio = fminf(1.0f, fmaxf(0.05f, (float)distinct / (float)tot));
       lo_id = hi_id;
+      jl = j_hi;
     }
     if (redo) continue;
     d0 += nd;
@@ -820,13 +983,14 @@ __device__ void pair_source(volatile S* tbl, const PairArgs& A, int dmin, int dl
 __global__ void __launch_bounds__(PC_WARPS * 32, 1)
 pair_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
                        const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
-                       const uint32_t* __restrict__ occ, int64_t n_kmers, int64_t a_begin, int64_t a_end,
-                       int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint4* cand,
-                       int64_t max_cand, int64_t* counters) {
+                       const uint32_t* __restrict__ occ, const uint32_t* __restrict__ usplit, int64_t n_kmers,
+                       int64_t a_begin, int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d,
+                       uint32_t min_cov, uint4* cand, int64_t max_cand, int64_t* counters) {
   extern __shared__ __align__(16) unsigned char pc_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* my_tbl = pc_smem + (size_t)warp * PC_TBL_BYTES;
+  const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(pc_smem) + (uint32_t)warp * PC_TBL_BYTES;
   const int dmin = max(min_d, 1);
+  min_cov = max(min_cov, 1u);  // the reference only ever looks at counters that exist, i.e. are >= 1 (dbkr.py:133-136)
   const int kb = 64 - __clzll((unsigned long long)n_kmers);  // bits of the largest key b + 1 = n_kmers
   int64_t incr_total = 0, splits = 0;
   float ratio = 1.0f;
@@ -884,12 +1048,12 @@ pair_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __r
       dlim = lo_d;
     }
     if (dlim < dmin) continue;
-    PairArgs A{unit_ptr, ids, unit_last, occ_a, m, n_kmers, a, min_cov, cand, max_cand, counters};
+    PairArgs A{unit_ptr, ids, unit_last, occ_a, usplit, m, n_kmers, a, min_cov, cand, max_cand, counters};
     const int mb = 64 - __clzll((unsigned long long)m);  // a single-distance count never exceeds m
     if (kb + mb <= 32 && (32 - kb) >= 8)
-      pair_source<uint32_t>((volatile uint32_t*)my_tbl, A, dmin, dlim, 32 - kb, ratio, splits);
+      pair_source<uint32_t>(tbase, A, dmin, dlim, 32 - kb, ratio, splits);
     else
-      pair_source<uint64_t>((volatile uint64_t*)my_tbl, A, dmin, dlim, 32, ratio, splits);
+      pair_source<uint64_t>(tbase, A, dmin, dlim, 32, ratio, splits);
   }
   if (lane == 0) {
     if (incr_total) atomicAdd((unsigned long long*)(counters + 2), (unsigned long long)incr_total);
@@ -1025,6 +1189,28 @@ int cfk_table_select(const uint64_t* t1_keys, const uint32_t* t1_nreads, const u
   return CFK_OK;
 }
 
+int cfk_table_part_count(const uint64_t* t1_keys, int64_t cap1, int32_t n_parts, int64_t* counts,
+                         cfk_stream_t stream) {
+  if (cap1 < 1 || n_parts < 1 || n_parts > TP_MAX_PARTS)
+    return fail(CFK_ERR_INVALID, "cfk_table_part_count: need cap1 >= 1 and 1 <= n_parts <= 64");
+  const int64_t nb = blocks_for(cap1, 256 * 8);
+  table_part_count_kernel<<<(unsigned)(nb < 1 ? 1 : nb), 256, 0, (cudaStream_t)stream>>>(t1_keys, cap1, n_parts, counts);
+  CFK_CHECK_LAUNCH("table_part_count_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_table_part_scatter(const uint64_t* t1_keys, const uint32_t* t1_nreads, const uint32_t* t1_nmulti, int64_t cap1,
+                           int32_t n_parts, int64_t* cursors, uint64_t* out_keys, uint32_t* out_nreads,
+                           uint32_t* out_nmulti, cfk_stream_t stream) {
+  if (cap1 < 1 || n_parts < 1 || n_parts > TP_MAX_PARTS)
+    return fail(CFK_ERR_INVALID, "cfk_table_part_scatter: need cap1 >= 1 and 1 <= n_parts <= 64");
+  const int64_t nb = blocks_for(cap1, 256 * 8);
+  table_part_scatter_kernel<<<(unsigned)(nb < 1 ? 1 : nb), 256, 0, (cudaStream_t)stream>>>(
+      t1_keys, t1_nreads, t1_nmulti, cap1, n_parts, cursors, out_keys, out_nreads, out_nmulti);
+  CFK_CHECK_LAUNCH("table_part_scatter_kernel", 1);
+  return CFK_OK;
+}
+
 int cfk_sort_u64(uint64_t* keys, int64_t n, cfk_stream_t stream) {
   if (n < 0) return fail(CFK_ERR_INVALID, "cfk_sort_u64: n < 0");
   if (n <= 1) return CFK_OK;
@@ -1147,10 +1333,24 @@ int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_str
   return CFK_OK;
 }
 
+int cfk_unit_splits(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, int64_t n_entries, int64_t n_kmers,
+                    uint32_t* usplit, cfk_stream_t stream) {
+  if (n_units < 0 || n_kmers < 0 || n_entries < 0 || n_entries >= (1ll << 32))
+    return fail(CFK_ERR_INVALID, "cfk_unit_splits: need 0 <= n_entries < 2^32");
+  if (n_units == 0) return CFK_OK;
+  unit_split_kernel<<<(unsigned)blocks_for(n_units * 7, 256), 256, 0, (cudaStream_t)stream>>>(unit_ptr, ids, n_units,
+                                                                                           n_kmers, usplit);
+  CFK_CHECK_LAUNCH("unit_split_kernel", 1);
+  return CFK_OK;
+}
+
 int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint32_t* unit_last,
-                        const int64_t* occ_ptr, const uint32_t* occ, int64_t n_kmers, int64_t a_begin, int64_t a_end,
-                        int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint32_t* cand,
-                        int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream) {
+                        const int64_t* occ_ptr, const uint32_t* occ, const uint32_t* usplit, int64_t n_entries,
+                        int64_t n_kmers, int64_t a_begin, int64_t a_end, int32_t a_stride, int32_t min_d,
+                        int32_t max_d, uint32_t min_cov, uint32_t* cand, int64_t max_cand, int64_t* counters,
+                        int32_t n_blocks, cfk_stream_t stream) {
+  if (n_entries < 0 || n_entries >= (1ll << 32))
+    return fail(CFK_ERR_INVALID, "cfk_pair_candidates: need 0 <= n_entries < 2^32 (32-bit positions in the id array)");
   if (n_kmers < 0 || n_kmers >= (1ll << 32) - 1) return fail(CFK_ERR_INVALID, "cfk_pair_candidates: bad n_kmers");
   if (min_d < 0) return fail(CFK_ERR_INVALID, "cfk_pair_candidates: min_d < 0 is not defined by the reference loop");
   if (a_begin < 0 || a_end > n_kmers || a_stride < 1) return fail(CFK_ERR_INVALID, "cfk_pair_candidates: bad id range");
@@ -1164,8 +1364,8 @@ int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint
     attr_done = true;
   }
   pair_candidates_kernel<<<(unsigned)n_blocks, PC_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      unit_ptr, ids, unit_last, occ_ptr, occ, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
-      max_cand, counters);
+      unit_ptr, ids, unit_last, occ_ptr, occ, usplit, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov,
+      (uint4*)cand, max_cand, counters);
   CFK_CHECK_LAUNCH("pair_candidates_kernel", 1);
   return CFK_OK;
 }

@@ -354,14 +354,18 @@ class Engine:
             return empty
         occ_ptr, occ = occurrences if occurrences is not None else self.build_occurrences(csr, n_kmers, unit_lo, unit_hi)
         min_cov_u = int(min(max(min_cov, 0), U32_MAX))
+        usplit = self._empty(7 * csr.n_units, t.int32)
+        _lib.call("cfk_unit_splits", self._p(csr.unit_ptr), self._p(csr.ids), csr.n_units, csr.n_entries, n_kmers,
+                  self._p(usplit), self._stream())
         max_cand = int(self.cand_hint)
         while True:
             cand = self._empty(max_cand * 4, t.int32)
             counters = self._counters()
             with self._stage("pair_candidates"):
                 _lib.call("cfk_pair_candidates", self._p(csr.unit_ptr), self._p(csr.ids), self._p(unit_last),
-                          self._p(occ_ptr), self._p(occ), n_kmers, a_begin, a_end, a_stride, int(min_d), int(max_d),
-                          min_cov_u, self._p(cand), max_cand, self._p(counters), self.n_sms, self._stream())
+                          self._p(occ_ptr), self._p(occ), self._p(usplit), csr.n_entries, n_kmers, a_begin, a_end,
+                          a_stride, int(min_d), int(max_d), min_cov_u, self._p(cand), max_cand, self._p(counters),
+                          self.n_sms, self._stream())
             c = counters.cpu()
             n_cand = int(c[0])
             if n_cand <= max_cand:

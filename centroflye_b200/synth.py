@@ -117,12 +117,13 @@ def _draw_lengths(rng, n, median, sigma, lo, hi):
 
 def simulate_reads(genome, array_start, array_len, motif, coverage, error_rate, seed,
                    median_len=35000, sigma=0.5, min_len=5000, max_len=300000,
-                   min_aligned=1, id_prefix="read"):
+                   min_aligned=1, id_prefix="read", shard=None):
     """Reads overlapping the array, with their truth alignment to the motif.
 
     Coverage is over the flanked genome; reads whose overlap with the array is
     shorter than ``min_aligned`` genome bases carry no alignment and are skipped
-    (NCRF would not report them).
+    (NCRF would not report them).  ``shard=(r, n)`` materialises only reads i with i % n == r of the
+    SAME read set (lengths, positions and per-read seeds are drawn for all reads first).
     """
     rng = np.random.default_rng(seed)
     motif_codes = ascii_to_codes(motif)
@@ -137,6 +138,8 @@ def simulate_reads(genome, array_start, array_len, motif, coverage, error_rate, 
     e3 = error_rate / 3.0
     reads = []
     for i in range(n_reads):
+        if shard is not None and i % shard[1] != shard[0]:
+            continue
         s = int(starts[i])
         e = min(G, s + int(lengths[i]))
         a0, a1 = max(s, a_lo), min(e, a_hi)

@@ -36,8 +36,12 @@ extern "C" {
 
 #define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define CFK_DOCFREQ_CHUNK 2048 /* k-mer start positions handled by one thread block */
-#define CFK_PAIR_WARPS 28         /* warps per block of the stage-C kernel (one block per SM) */
-#define CFK_PAIR_TABLE_BYTES 8192 /* shared-memory counting table of one warp */
+#ifndef CFK_PAIR_WARPS
+#define CFK_PAIR_WARPS 20         /* warps per block of the stage-C kernel (one block per SM) */
+#endif
+#ifndef CFK_PAIR_TABLE_BYTES
+#define CFK_PAIR_TABLE_BYTES 11264 /* shared-memory counting table of one warp (multiple of 16) */
+#endif
 
 typedef void* cfk_stream_t;
 
@@ -82,6 +86,19 @@ int cfk_table_select(const uint64_t* t1_keys, const uint32_t* t1_nreads, const u
                      uint32_t lo, uint32_t hi, uint32_t max_nonuniq, int32_t n_parts, int32_t part,
                      uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out,
                      int64_t* counters, cfk_stream_t stream);
+
+/* Hash partition of a whole table for the multi-GPU exchange: every occupied
+ * slot goes to partition owner(key) = mix64(key ^ 0x9E3779B97F4A7C15) % n_parts (the rule
+ * cfk_table_select applies), n_parts <= 64.  cfk_table_part_count adds the partition sizes to
+ * counts[n_parts] (zeroed by the caller); cfk_table_part_scatter writes the records so that
+ * partition p occupies [cursors[p], cursors[p] + count[p]) of the output arrays -- cursors
+ * holds the exclusive prefix of the counts on entry and the end offsets on return.  This is the
+ * send buffer layout of the NCCL all-to-all; the receiver feeds cfk_table_merge. */
+int cfk_table_part_count(const uint64_t* t1_keys, int64_t cap1, int32_t n_parts, int64_t* counts,
+                         cfk_stream_t stream);
+int cfk_table_part_scatter(const uint64_t* t1_keys, const uint32_t* t1_nreads, const uint32_t* t1_nmulti,
+                           int64_t cap1, int32_t n_parts, int64_t* cursors, uint64_t* out_keys,
+                           uint32_t* out_nreads, uint32_t* out_nmulti, cfk_stream_t stream);
 
 /* In-place ascending sort of n uint64 keys (bitonic network, shared-memory tiles).  The rank
  * of a k-mer in the sorted rare set is its integer id everywhere downstream (the reference's
@@ -131,6 +148,12 @@ int cfk_occ_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, 
                  const int64_t* occ_ptr, int32_t* cursor, uint32_t* occ, cfk_stream_t stream);
 int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_stream_t stream);
 
+/* usplit[7 u + j - 1] (j = 1..7) = position in ids[] of the first id of unit u that is
+ * >= (n_kmers * j) >> 3: the per-unit octant split table cfk_pair_candidates uses to cut a unit
+ * list by id range without searching (uint32[7 n_units]; n_entries < 2^32). */
+int cfk_unit_splits(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, int64_t n_entries, int64_t n_kmers,
+                    uint32_t* usplit, cfk_stream_t stream);
+
 /* Replaces the counting loop of get_kmer_dist_map, distance_based_kmer_recruitment.py:111-127,
  * fused with the candidate pass of filter_dist_tuples (:133-138).  The reference keeps one
  * counter per (d, a, b); here every source id a (a_begin, a_begin + a_stride, ... < a_end) is
@@ -139,14 +162,15 @@ int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_str
  * emits the pair candidate (a, b, d0, d1) as 4 x uint32 whenever that sum reaches min_cov -- a
  * necessary condition for cnt[d][a][b] >= min_cov at some d of the chunk.  Every (a, b, d)
  * belongs to exactly one emitted or rejected chunk, so cfk_pair_join sees each possible edge once.
- * unit_last[g] = index of the last unit of g's read.
+ * unit_last[g] = index of the last unit of g's read; usplit = cfk_unit_splits output or NULL
+ * (binary search instead); n_entries = unit_ptr[n_units] must be < 2^32.
  * counters (zeroed by the caller): [0] candidates found (also beyond max_cand; nothing is
  * written past max_cand), [1] dynamic work cursor, [2] pair increments (the reference's number
  * of `+= 1` executions at :126, in closed form), [3] table overflows that forced a smaller chunk.
  */
 int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint32_t* unit_last,
-                        const int64_t* occ_ptr, const uint32_t* occ, int64_t n_kmers,
-                        int64_t a_begin, int64_t a_end, int32_t a_stride,
+                        const int64_t* occ_ptr, const uint32_t* occ, const uint32_t* usplit, int64_t n_entries,
+                        int64_t n_kmers, int64_t a_begin, int64_t a_end, int32_t a_stride,
                         int32_t min_d, int32_t max_d, uint32_t min_cov,
                         uint32_t* cand, int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
 

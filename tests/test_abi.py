@@ -48,7 +48,8 @@ def test_argument_validation_without_gpu(lib_path):
     with pytest.raises(_lib.CfkError, match="k must be"):
         _lib.call("cfk_docfreq_count", None, None, None, None, 1, 1, 0, 32, None, None, None, 10, None, 10, None, None)
     with pytest.raises(_lib.CfkError, match="min_d"):
-        _lib.call("cfk_pair_candidates", None, None, None, None, None, 10, 0, 10, 1, -1, 5, 1, None, 0, None, 1, None)
+        _lib.call("cfk_pair_candidates", None, None, None, None, None, None, 5, 10, 0, 10, 1, -1, 5, 1, None, 0, None, 1,
+                  None)
     assert b"min_d" in lib.cfk_last_error()
 
 

@@ -212,3 +212,18 @@ def test_non_acgt_is_rejected_loudly(mods, tmp_path):
     with pytest.raises(ValueError):
         dbkr.get_rare_kmers(NCRF_Report(str(path)), k=19, bottom=0.9, top=3.0, coverage=6, kmer_survival_rate=0.5,
                             max_nonuniq=3, verbose=False)
+
+
+def test_sharded_recruitment_two_gpus():
+    """One process per GPU over NCCL: sharded path == CPU oracle on the whole read set (skipped with < 2 GPUs)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(root, "tools", "multi_gpu_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert "multi-gpu ok" in out.stdout

@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""Run under torchrun (one rank per GPU): sharded recruitment == the CPU oracle on the whole read set.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multi_gpu_check.py
+
+Checks (rank 0): identical rare set, identical edge set, identical unique k-mers, identical increment count; every
+rank: its own clouds equal the oracle's clouds of its reads.  Test infrastructure (uses oracle/)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    from centroflye_b200 import synth
+    from centroflye_b200.dist import ShardedRecruiter
+    from centroflye_b200.engine import Engine, band_to_int
+    from centroflye_b200.ingest import batch_from_synth
+    from oracle import c_oracle
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    eng = Engine(f"cuda:{local}")
+    unit = synth.hor_unit(4, 60, 0.25, seed=5)
+    genome, a0, alen = synth.simulate_genome(unit, 160, 0.02, 6, flank_len=2000)
+    kw = dict(median_len=7000, sigma=0.4, min_len=5200, max_len=20000)
+    reads = synth.simulate_reads(genome, a0, alen, unit, 20, 0.05, 7, **kw)
+    mine = synth.simulate_reads(genome, a0, alen, unit, 20, 0.05, 7, shard=(rank, world), **kw)
+    assert [r.r_id for r in mine] == [r.r_id for r in reads[rank::world]]
+    k, max_nonuniq, min_d, max_d, min_cov = 19, 3, 1, 150, 4
+    lo, hi = band_to_int(0.9 * 20 * 0.4, 3.0 * 20 * 0.4)
+    batch, units = batch_from_synth(mine, len(unit))
+    rec = ShardedRecruiter(eng, batch, units, k, rank, world)
+    index, csr, res = rec.step(lo, hi, max_nonuniq, min_d, max_d, min_cov)
+    keys = index.sorted_keys.cpu().numpy().view(np.uint64)
+
+    whole_batch, whole_units = batch_from_synth(reads, len(unit))
+    want = c_oracle.recruit(whole_batch, whole_units, k, lo, hi, max_nonuniq, min_d, max_d, min_cov, threads=2)
+    assert np.array_equal(keys, want["rare"]), "rare set differs"
+    my_ptr, my_ids = c_oracle.clouds(c_oracle.unpacked_codes(batch), units, k, want["rare"])
+    assert np.array_equal(csr.unit_ptr.cpu().numpy()[: units.n_units + 1], my_ptr), "local cloud sizes differ"
+    assert np.array_equal(csr.ids.cpu().numpy().view(np.uint32)[: my_ids.size], my_ids), "local clouds differ"
+    assert res.n_increments == want["n_increments"], (res.n_increments, want["n_increments"])
+    got = res.edges.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    canon = lambda e: e[np.lexsort((e[:, 3], e[:, 2], e[:, 1], e[:, 0]))]  # noqa: E731
+    assert np.array_equal(canon(got), canon(want["edges"])), "edge set differs"
+    assert np.array_equal(np.sort(res.selected.cpu().numpy().view(np.uint32)), want["selected"]), "unique k-mers differ"
+    dist.barrier()
+    if rank == 0:
+        print(f"multi-gpu ok: world={world}, {rec.n_bases_total} read bases, {keys.size} rare k-mers, "
+              f"{got.shape[0]} edges, {res.selected.numel()} unique k-mers, {rec.bytes_exchanged} bytes sent by rank 0")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
