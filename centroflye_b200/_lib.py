@@ -21,11 +21,12 @@ SIGNATURES = {
     "cfk_pair_table_bytes_per_warp": (_int, []),
     "cfk_pair_warps_per_block": (_int, []),
     "cfk_launch_count": (_i64, []),
-    "cfk_docfreq_count": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, _p, _p, _p, _i64, _p, _i64, _p, _p]),
-    "cfk_table_merge": (_int, [_p, _p, _p, _i64, _p, _p, _p, _i64, _p, _p]),
-    "cfk_table_select": (_int, [_p, _p, _p, _i64, _u32, _u32, _u32, _i32, _i32, _p, _p, _p, _i64, _p, _p]),
+    "cfk_table_init": (_int, [_p, _i64, _p]),
+    "cfk_docfreq_count": (_int, [_p, _p, _p, _p, _i64, _int, _p, _i64, _p, _i32, _p]),
+    "cfk_table_merge": (_int, [_p, _p, _p, _i64, _p, _i64, _p, _p]),
+    "cfk_table_select": (_int, [_p, _i64, _u32, _u32, _u32, _i32, _i32, _p, _p, _p, _i64, _p, _p]),
     "cfk_table_part_count": (_int, [_p, _i64, _i32, _p, _p]),
-    "cfk_table_part_scatter": (_int, [_p, _p, _p, _i64, _i32, _p, _p, _p, _p, _p]),
+    "cfk_table_part_scatter": (_int, [_p, _i64, _i32, _p, _p, _p, _p, _p]),
     "cfk_sort_u64": (_int, [_p, _i64, _p]),
     "cfk_index_build": (_int, [_p, _i64, _p, _p, _i64, _p, _p]),
     "cfk_cloud_build": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _i64, _p, _p, _p]),

@@ -82,93 +82,146 @@ __device__ __forceinline__ int64_t table_find(const uint64_t* __restrict__ keys,
 }
 
 // ============================================================================================
-// Stage A: document frequency.  One block = CFK_DOCFREQ_CHUNK consecutive k-mer starts of one
-// read, staged through shared memory; each thread rolls 8 consecutive k-mers.
-//   t1: kmer -> slot (dense id), with per-slot n_reads / n_multi
-//   t2: (slot, read) pair set, bit 0 = "seen twice in this read"
+// Stage A: document frequency.
+//
+// Global table: open addressing over 16-byte slots { u64 key ; u32 n_reads ; u32 n_multi } (one
+// 32-byte DRAM sector holds two slots, so a key probe and its counter update touch one sector).
+// Per-read de-duplication happens in SHARED memory, so the global table sees one update per
+// distinct (read, k-mer) instead of one per occurrence: one persistent block per read (longest
+// reads first) keeps a set of the read's k-mers as 32-bit slots holding the POSITION of the
+// k-mer's first occurrence (+1) and a "seen again" bit; equality of two k-mers is checked by
+// re-extracting the stored position's k-mer from the packed read.  Reads whose k-mers do not fit
+// the set in one go are processed in several passes over disjoint hash partitions of the k-mer
+// space.  The first sighting of a k-mer in a read adds 1 to n_reads, the second adds 1 to n_multi
+// (exactly once: the thread that flips the "seen again" bit).
 // ============================================================================================
-constexpr int DF_THREADS = 256;
-constexpr int DF_PER_THREAD = CFK_DOCFREQ_CHUNK / DF_THREADS;
-constexpr int DF_WORDS = (CFK_DOCFREQ_CHUNK + 32 + 15) / 16 + 2;
+constexpr int DF_THREADS = 1024;
+constexpr int DF_PER_THREAD = 8;
+constexpr int DF_TILE = DF_THREADS * DF_PER_THREAD;  // k-mer starts staged per tile
+constexpr int DF_TILE_WORDS = DF_TILE / 16 + 4;       // + up to 30 bases of overlap
+constexpr int DF_SET_SLOTS = CFK_DOCFREQ_SET_SLOTS;   // u32 slots of the per-read set
+constexpr int DF_SET_FILL = DF_SET_SLOTS * 53 / 100;  // k-mers planned per pass
+constexpr uint32_t DF_MULTI = 0x80000000u;
 
-__global__ void __launch_bounds__(DF_THREADS)
+// find-or-insert in the global table; returns the slot or -1 if full
+__device__ __forceinline__ int64_t slot_upsert(uint64_t* table, int64_t cap, uint64_t key, uint64_t h) {
+  int64_t slot = home_slot(h, cap);
+  for (int64_t probes = 0; probes < cap; ++probes) {
+    const uint64_t cur = ((volatile uint64_t*)table)[2 * slot];
+    if (cur == key) return slot;
+    if (cur == EMPTY) {
+      const unsigned long long old = atomicCAS((unsigned long long*)(table + 2 * slot), (unsigned long long)EMPTY,
+                                               (unsigned long long)key);
+      if (old == EMPTY || old == key) return slot;
+    }
+    if (++slot == cap) slot = 0;
+  }
+  return -1;
+}
+
+// k-mer starting at base q of a packed read (words = word holding the read's base 0)
+__device__ __forceinline__ uint64_t kmer_at(const uint32_t* __restrict__ words, uint32_t q, int k) {
+  const uint32_t w = q >> 4, sh = (q & 15u) << 1;
+  uint64_t bits = ((uint64_t)__ldg(words + w) | ((uint64_t)__ldg(words + w + 1) << 32)) >> sh;
+  if (sh) bits |= (uint64_t)__ldg(words + w + 2) << (64 - sh);
+  // base q + j sits at bits 2j..2j+1; the k-mer wants base q in its top bits: reverse the 2-bit groups
+  uint64_t r = __brevll(bits);
+  r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
+  return r >> (64 - 2 * k);
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 1)
 docfreq_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ read_off,
-               const int64_t* __restrict__ read_len, const int64_t* __restrict__ chunk_ptr, int64_t n_reads,
-               int64_t read_id_base, int k, uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti,
-               int64_t cap1, uint64_t* t2_pairs, int64_t cap2, int64_t* counters) {
-  __shared__ uint32_t s_words[DF_WORDS];
-  __shared__ int64_t s_read;
-  const int64_t chunk = blockIdx.x;
-  if (threadIdx.x == 0) {
-    int64_t lo = 0, hi = n_reads;  // last r with chunk_ptr[r] <= chunk
-    while (hi - lo > 1) {
-      int64_t mid = (lo + hi) >> 1;
-      if (chunk_ptr[mid] <= chunk) lo = mid; else hi = mid;
-    }
-    s_read = lo;
-  }
-  __syncthreads();
-  const int64_t r = s_read;
-  const int64_t pos0 = (chunk - chunk_ptr[r]) * CFK_DOCFREQ_CHUNK;
-  const int64_t nk = read_len[r] - k + 1;
-  const int npos = (int)min((int64_t)CFK_DOCFREQ_CHUNK, nk - pos0);
-  if (npos <= 0) return;
-  const int64_t word0 = (read_off[r] + pos0) >> 4;  // read_off % 64 == 0 and pos0 % 2048 == 0
-  const int nwords = (npos + k - 1 + 15) >> 4;
-  for (int i = threadIdx.x; i < nwords; i += DF_THREADS) s_words[i] = __ldg(packed + word0 + i);
-  __syncthreads();
-
-  const int p0 = threadIdx.x * DF_PER_THREAD;
-  if (p0 >= npos) return;
-  const uint64_t mask = (k == 32) ? ~0ull : ((1ull << (2 * k)) - 1);
-  const uint64_t read_bits = (uint64_t)(read_id_base + r) << 1;
-  uint64_t kmer = 0;
-  for (int i = 0; i < k - 1; ++i) {
-    int p = p0 + i;
-    kmer = (kmer << 2) | ((s_words[p >> 4] >> ((p & 15) << 1)) & 3u);
-  }
-  const int pend = min(p0 + DF_PER_THREAD, npos);
-  for (int p = p0; p < pend; ++p) {
-    int q = p + k - 1;
-    kmer = ((kmer << 2) | ((s_words[q >> 4] >> ((q & 15) << 1)) & 3u)) & mask;
-    int64_t slot = table_upsert(t1_keys, cap1, kmer);
-    if (slot < 0) { counters[0] = 1; return; }
-    const uint64_t pk = ((uint64_t)slot << 32) | read_bits;
-    int64_t s2 = home_slot(mix64(pk), cap2);
-    int64_t probes = 0;
-    for (; probes < cap2; ++probes) {
-      uint64_t cur = ((volatile uint64_t*)t2_pairs)[s2];
-      if (cur == EMPTY) {
-        unsigned long long old = atomicCAS((unsigned long long*)(t2_pairs + s2), (unsigned long long)EMPTY,
-                                           (unsigned long long)pk);
-        if (old == EMPTY) {  // first sighting of this k-mer in this read
-          atomicAdd(t1_nreads + slot, 1u);
-          break;
+               const int64_t* __restrict__ read_len, const int32_t* __restrict__ order, int64_t n_reads, int k,
+               uint64_t* table, int64_t cap, int64_t* counters) {
+  extern __shared__ __align__(16) uint32_t df_smem[];
+  uint32_t* set = df_smem;                   // [DF_SET_SLOTS]
+  uint32_t* s_words = df_smem + DF_SET_SLOTS;  // [DF_TILE_WORDS]
+  __shared__ long long s_item;
+  const uint64_t mask = (1ull << (2 * k)) - 1;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = (long long)atomicAdd((unsigned long long*)(counters + 2), 1ull);
+    __syncthreads();
+    const int64_t item = s_item;
+    if (item >= n_reads) break;
+    const int64_t r = order[item];
+    const int64_t nk = read_len[r] - k + 1;
+    if (nk <= 0) continue;
+    const uint32_t* words = packed + (read_off[r] >> 4);  // every read starts on a 64-base boundary
+    const uint32_t n_pass = (uint32_t)((nk + DF_SET_FILL - 1) / DF_SET_FILL);
+    const uint32_t c_eff = (n_pass > 1) ? (uint32_t)DF_SET_SLOTS
+                                        : (uint32_t)min((int64_t)DF_SET_SLOTS, max((int64_t)2048, 2 * nk));
+    for (uint32_t pass = 0; pass < n_pass; ++pass) {
+      __syncthreads();
+      for (uint32_t i = threadIdx.x * 4; i < c_eff; i += DF_THREADS * 4)  // c_eff is a multiple of 4 or the full set
+        *reinterpret_cast<uint4*>(set + i) = make_uint4(0, 0, 0, 0);
+      for (int64_t tile0 = 0; tile0 < nk; tile0 += DF_TILE) {
+        const int npos = (int)min((int64_t)DF_TILE, nk - tile0);
+        const int nwords = (npos + k - 1 + 15) >> 4;
+        __syncthreads();  // set cleared / previous tile consumed
+        for (int i = threadIdx.x; i < nwords; i += DF_THREADS) s_words[i] = __ldg(words + (tile0 >> 4) + i);
+        __syncthreads();
+        const int p0 = threadIdx.x * DF_PER_THREAD;
+        if (p0 >= npos) continue;
+        uint64_t kmer = 0;
+        for (int i = 0; i < k - 1; ++i) {
+          const int p = p0 + i;
+          kmer = (kmer << 2) | ((s_words[p >> 4] >> ((p & 15) << 1)) & 3u);
         }
-        cur = old;
-      }
-      if ((cur & ~1ull) == pk) {
-        if (!(cur & 1ull)) {
-          unsigned long long old = atomicOr((unsigned long long*)(t2_pairs + s2), 1ull);
-          if (!(old & 1ull)) atomicAdd(t1_nmulti + slot, 1u);  // exactly one thread sees the 0 -> 1 flip
+        const int pend = min(p0 + DF_PER_THREAD, npos);
+        for (int p = p0; p < pend; ++p) {
+          const int q = p + k - 1;
+          kmer = ((kmer << 2) | ((s_words[q >> 4] >> ((q & 15) << 1)) & 3u)) & mask;
+          if (n_pass > 1 && __umulhi((uint32_t)(kmer ^ (kmer >> 32)) * 0x9E3779B1u, n_pass) != pass) continue;
+          const uint64_t h = mix64(kmer);
+          const uint32_t pos = (uint32_t)(tile0 + p);
+          uint32_t s = __umulhi((uint32_t)h, c_eff);
+          uint32_t probes = 0;
+          for (; probes < c_eff; ++probes) {
+            uint32_t v = ((volatile uint32_t*)set)[s];
+            if (v == 0) {
+              v = atomicCAS(set + s, 0u, pos + 1);
+              if (v == 0) {  // first sighting of this k-mer in this read
+                const int64_t slot = slot_upsert(table, cap, kmer, h);
+                if (slot < 0) counters[0] = 1;
+                else atomicAdd(reinterpret_cast<uint32_t*>(table + 2 * slot + 1), 1u);
+                break;
+              }
+            }
+            if (kmer_at(words, (v & ~DF_MULTI) - 1, k) == kmer) {
+              if (!(v & DF_MULTI) && !(atomicOr(set + s, DF_MULTI) & DF_MULTI)) {  // exactly one thread flips the bit
+                const int64_t slot = slot_upsert(table, cap, kmer, h);
+                if (slot < 0) counters[0] = 1;
+                else atomicAdd(reinterpret_cast<uint32_t*>(table + 2 * slot + 1) + 1, 1u);
+              }
+              break;
+            }
+            if (++s == c_eff) s = 0;
+          }
+          if (probes == c_eff) counters[1] = 1;  // cannot happen: a pass is planned for <= 53 % load
         }
-        break;
       }
-      if (++s2 == cap2) s2 = 0;
     }
-    if (probes == cap2) { counters[1] = 1; return; }
   }
 }
 
+__global__ void table_init_kernel(uint64_t* table, int64_t cap) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cap) reinterpret_cast<ulonglong2*>(table)[i] = make_ulonglong2(EMPTY, 0ull);
+}
+
 __global__ void table_merge_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ nreads,
-                                   const uint32_t* __restrict__ nmulti, int64_t n, uint64_t* t1_keys,
-                                   uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1, int64_t* counters) {
+                                   const uint32_t* __restrict__ nmulti, int64_t n, uint64_t* table, int64_t cap,
+                                   int64_t* counters) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int64_t slot = table_upsert(t1_keys, cap1, keys[i]);
+  const uint64_t key = keys[i];
+  int64_t slot = slot_upsert(table, cap, key, mix64(key));
   if (slot < 0) { counters[0] = 1; return; }
-  if (nreads[i]) atomicAdd(t1_nreads + slot, nreads[i]);
-  if (nmulti[i]) atomicAdd(t1_nmulti + slot, nmulti[i]);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(table + 2 * slot + 1);
+  if (nreads[i]) atomicAdd(cnt, nreads[i]);
+  if (nmulti[i]) atomicAdd(cnt + 1, nmulti[i]);
 }
 
 // warp-aggregated append: returns the output position of this lane's item, or -1
@@ -183,21 +236,25 @@ __device__ __forceinline__ int64_t warp_append(bool take, int64_t* counter) {
   return take ? (int64_t)base + __popc(m & ((1u << lane) - 1)) : -1;
 }
 
-__global__ void table_select_kernel(const uint64_t* __restrict__ t1_keys, const uint32_t* __restrict__ t1_nreads,
-                                    const uint32_t* __restrict__ t1_nmulti, int64_t cap1, uint32_t lo, uint32_t hi,
+__device__ __forceinline__ int32_t key_owner(uint64_t key, int32_t n_parts) {
+  return (int32_t)(mix64(key ^ 0x9E3779B97F4A7C15ull) % (uint64_t)n_parts);
+}
+
+__global__ void table_select_kernel(const uint64_t* __restrict__ table, int64_t cap, uint32_t lo, uint32_t hi,
                                     uint32_t max_nonuniq, int32_t n_parts, int32_t part, uint64_t* out_keys,
                                     uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out, int64_t* counters) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool take = false;
   uint64_t key = 0;
   uint32_t nr = 0, nm = 0;
-  if (i < cap1) {
-    key = t1_keys[i];
+  if (i < cap) {
+    const ulonglong2 s = reinterpret_cast<const ulonglong2*>(table)[i];
+    key = s.x;
     if (key != EMPTY) {
-      nr = t1_nreads[i];
-      nm = t1_nmulti[i];
+      nr = (uint32_t)s.y;
+      nm = (uint32_t)(s.y >> 32);
       take = nm <= max_nonuniq && nr >= lo && nr <= hi;
-      if (take && n_parts > 0) take = (int32_t)(mix64(key ^ 0x9E3779B97F4A7C15ull) % (uint64_t)n_parts) == part;
+      if (take && n_parts > 0) take = key_owner(key, n_parts) == part;
     }
   }
   int64_t pos = warp_append(take, counters);
@@ -210,19 +267,15 @@ __global__ void table_select_kernel(const uint64_t* __restrict__ t1_keys, const 
 
 // ---- hash partition of a table for the multi-GPU exchange --------------------------------------
 // owner(key) = mix64(key ^ golden) % n_parts -- the same rule table_select_kernel applies.
-__device__ __forceinline__ int32_t key_owner(uint64_t key, int32_t n_parts) {
-  return (int32_t)(mix64(key ^ 0x9E3779B97F4A7C15ull) % (uint64_t)n_parts);
-}
-
 constexpr int TP_MAX_PARTS = 64;
 
-__global__ void __launch_bounds__(256) table_part_count_kernel(const uint64_t* __restrict__ t1_keys, int64_t cap1,
+__global__ void __launch_bounds__(256) table_part_count_kernel(const uint64_t* __restrict__ table, int64_t cap,
                                                               int32_t n_parts, int64_t* counts) {
   __shared__ int s_cnt[TP_MAX_PARTS];
   if (threadIdx.x < TP_MAX_PARTS) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap1; i += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t key = t1_keys[i];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = table[2 * i];
     if (key != EMPTY) atomicAdd(&s_cnt[key_owner(key, n_parts)], 1);
   }
   __syncthreads();
@@ -232,19 +285,17 @@ __global__ void __launch_bounds__(256) table_part_count_kernel(const uint64_t* _
 
 // cursors[p] starts at the first output index of partition p; records of one partition end up
 // contiguous (in arbitrary order), which is the send layout of the all-to-all.
-__global__ void __launch_bounds__(256) table_part_scatter_kernel(const uint64_t* __restrict__ t1_keys,
-                                                                const uint32_t* __restrict__ t1_nreads,
-                                                                const uint32_t* __restrict__ t1_nmulti, int64_t cap1,
+__global__ void __launch_bounds__(256) table_part_scatter_kernel(const uint64_t* __restrict__ table, int64_t cap,
                                                                 int32_t n_parts, int64_t* cursors, uint64_t* out_keys,
                                                                 uint32_t* out_nreads, uint32_t* out_nmulti) {
   const int lane = threadIdx.x & 31;
-  const int64_t n_iter = (cap1 + (int64_t)gridDim.x * blockDim.x - 1) / ((int64_t)gridDim.x * blockDim.x);
+  const int64_t n_iter = (cap + (int64_t)gridDim.x * blockDim.x - 1) / ((int64_t)gridDim.x * blockDim.x);
   for (int64_t it = 0; it < n_iter; ++it) {  // every lane runs every iteration (warp collectives below)
     const int64_t i = (it * gridDim.x + blockIdx.x) * (int64_t)blockDim.x + threadIdx.x;
-    uint64_t key = EMPTY;
-    if (i < cap1) key = t1_keys[i];
-    const bool valid = key != EMPTY;
-    const int32_t p = valid ? key_owner(key, n_parts) : -1;
+    ulonglong2 s = make_ulonglong2(EMPTY, 0ull);
+    if (i < cap) s = reinterpret_cast<const ulonglong2*>(table)[i];
+    const bool valid = s.x != EMPTY;
+    const int32_t p = valid ? key_owner(s.x, n_parts) : -1;
     const unsigned peers = __match_any_sync(FULL, p);
     const int leader = __ffs(peers) - 1;
     unsigned long long base = 0;
@@ -252,9 +303,9 @@ __global__ void __launch_bounds__(256) table_part_scatter_kernel(const uint64_t*
     base = __shfl_sync(FULL, base, leader);
     if (valid) {
       const int64_t pos = (int64_t)base + __popc(peers & ((1u << lane) - 1));
-      out_keys[pos] = key;
-      out_nreads[pos] = t1_nreads[i];
-      out_nmulti[pos] = t1_nmulti[i];
+      out_keys[pos] = s.x;
+      out_nreads[pos] = (uint32_t)s.y;
+      out_nmulti[pos] = (uint32_t)(s.y >> 32);
     }
   }
 }
@@ -663,6 +714,23 @@ constexpr int PC_WARPS = CFK_PAIR_WARPS;
 constexpr int PC_TBL_BYTES = CFK_PAIR_TABLE_BYTES;
 constexpr uint32_t PC_NONE = 0xFFFFFFFFu;
 
+constexpr bool pc_is_prime(uint32_t n) {
+  if (n < 2) return false;
+  for (uint32_t d = 2; d * d <= n; ++d)
+    if (n % d == 0) return false;
+  return true;
+}
+constexpr uint32_t pc_prime_le(uint32_t n) { return pc_is_prime(n) ? n : pc_prime_le(n - 1); }
+// Slots used of a warp's table: the largest prime that fits, so that double hashing
+// (slot += step, any step in [1, NS - 1]) visits every slot.  Linear probing's long clusters
+// are poison here: a step of the warp costs the LONGEST probe chain among its 64 keys.
+template <typename S>
+struct PairTable {
+  static constexpr uint32_t NS = pc_prime_le(PC_TBL_BYTES / (uint32_t)sizeof(S));
+};
+__device__ __forceinline__ uint32_t pc_slot(uint32_t b, uint32_t ns) { return __umulhi(b * 2654435761u, ns); }
+__device__ __forceinline__ uint32_t pc_step(uint32_t b, uint32_t ns) { return 1u + __umulhi(b * 0x85EBCA77u + 0x9E3779B9u, ns - 1u); }
+
 struct PairArgs {
   const int64_t* __restrict__ unit_ptr;
   const uint32_t* __restrict__ ids;
@@ -707,16 +775,22 @@ struct PairLane {      // per-lane insert state carried from one step to the nex
   uint32_t vaddr[2];   // shared addresses of the not yet verified claims, PC_NONE = none
   S vword[2];          // what the claims wrote
   int claims;          // slots this lane has claimed in the current pass
+#ifdef CFK_PAIR_STATS
+  long long st_iters = 0, st_keys = 0, st_windows = 0;
+#endif
 };
 
 // One insert step: every lane counts up to two ids (all ids of a step are distinct).  Probes until
 // each key is counted or an empty slot is claimed; per-lane loop, no votes inside, the two
 // probe chains of a lane are independent (ILP).
 template <typename S>
-__device__ __forceinline__ void pair_probe2(uint32_t tbase, PairLane<S>& L, S key0, uint32_t h0, bool v0, S key1,
-                                            uint32_t h1, bool v1, int cb) {
-  constexpr uint32_t NS = PC_TBL_BYTES / (uint32_t)sizeof(S);
+__device__ __forceinline__ void pair_probe2(uint32_t tbase, PairLane<S>& L, S key0, uint32_t h0, uint32_t s0, bool v0,
+                                            S key1, uint32_t h1, uint32_t s1, bool v1, int cb) {
+  constexpr uint32_t NS = PairTable<S>::NS;
   while (v0 || v1) {
+#ifdef CFK_PAIR_STATS
+    ++L.st_iters;
+#endif
     const uint32_t a0 = tbase + h0 * (uint32_t)sizeof(S), a1 = tbase + h1 * (uint32_t)sizeof(S);
     S w0 = 0, w1 = 0;
     if (v0) w0 = lds<S>(a0);
@@ -733,7 +807,8 @@ __device__ __forceinline__ void pair_probe2(uint32_t tbase, PairLane<S>& L, S ke
         ++L.claims;
         v0 = false;
       } else {
-        h0 = (h0 + 1 == NS) ? 0u : h0 + 1;
+        h0 += s0;
+        if (h0 >= NS) h0 -= NS;
       }
     }
     if (v1) {
@@ -748,7 +823,8 @@ __device__ __forceinline__ void pair_probe2(uint32_t tbase, PairLane<S>& L, S ke
         ++L.claims;
         v1 = false;
       } else {
-        h1 = (h1 + 1 == NS) ? 0u : h1 + 1;
+        h1 += s1;
+        if (h1 >= NS) h1 -= NS;
       }
     }
   }
@@ -758,19 +834,23 @@ __device__ __forceinline__ void pair_probe2(uint32_t tbase, PairLane<S>& L, S ke
 // the same slot re-inserts its key (rare).
 template <typename S>
 __device__ __forceinline__ void pair_verify(uint32_t tbase, PairLane<S>& L, int cb) {
-  constexpr uint32_t NS = PC_TBL_BYTES / (uint32_t)sizeof(S);
+  constexpr uint32_t NS = PairTable<S>::NS;
   __syncwarp();
   bool lost0 = false, lost1 = false;
   if (L.vaddr[0] != PC_NONE) lost0 = lds<S>(L.vaddr[0]) != L.vword[0];
   if (L.vaddr[1] != PC_NONE) lost1 = lds<S>(L.vaddr[1]) != L.vword[1];
   while (__any_sync(FULL, lost0 || lost1)) {  // replay round: the losers hold distinct keys, nobody else inserts
-    uint32_t h0 = (L.vaddr[0] - tbase) / (uint32_t)sizeof(S) + 1, h1 = (L.vaddr[1] - tbase) / (uint32_t)sizeof(S) + 1;
-    if (h0 >= NS) h0 = 0;
-    if (h1 >= NS) h1 = 0;
+    const S k0 = L.vword[0] >> cb, k1 = L.vword[1] >> cb;
+    const uint32_t s0 = pc_step((uint32_t)k0 - 1u, NS), s1 = pc_step((uint32_t)k1 - 1u, NS);
+    uint32_t h0 = (L.vaddr[0] - tbase) / (uint32_t)sizeof(S) + s0, h1 = (L.vaddr[1] - tbase) / (uint32_t)sizeof(S) + s1;
+    if (h0 >= NS) h0 -= NS;
+    if (h1 >= NS) h1 -= NS;
+    if (!lost0) h0 = 0;
+    if (!lost1) h1 = 0;
     L.vaddr[0] = PC_NONE;
     L.vaddr[1] = PC_NONE;
     L.claims -= (int)lost0 + (int)lost1;
-    pair_probe2<S>(tbase, L, (S)(L.vword[0] >> cb), h0, lost0, (S)(L.vword[1] >> cb), h1, lost1, cb);
+    pair_probe2<S>(tbase, L, k0, h0, s0, lost0, k1, h1, s1, lost1, cb);
     __syncwarp();
     lost0 = lost0 && L.vaddr[0] != PC_NONE && lds<S>(L.vaddr[0]) != L.vword[0];
     lost1 = lost1 && L.vaddr[1] != PC_NONE && lds<S>(L.vaddr[1]) != L.vword[1];
@@ -792,7 +872,7 @@ __device__ __forceinline__ uint32_t split_pos(const PairArgs& A, int64_t u, int 
 template <typename S>
 __device__ int pair_chunk_pass(uint32_t tbase, const PairArgs& A, int d0, int d1, int64_t lo_id, int64_t hi_id, int j_lo,
                                int j_hi, int cb) {
-  constexpr uint32_t NS = PC_TBL_BYTES / (uint32_t)sizeof(S);
+  constexpr uint32_t NS = PairTable<S>::NS;
   constexpr int MAXLOAD = (int)(NS / 2);
   const int lane = threadIdx.x & 31;
   const bool whole = (lo_id == 0 && hi_id >= A.n_kmers);
@@ -858,10 +938,14 @@ __device__ int pair_chunk_pass(uint32_t tbase, const PairArgs& A, int d0, int d1
           if (np + 32u + lane < ne) n1 = __ldg(A.ids + np + 32u + lane);
         }
         pair_verify<S>(tbase, L, cb);
+#ifdef CFK_PAIR_STATS
+        L.st_keys += (b0 != A.a) + (b1 != A.a);
+        ++L.st_windows;
+#endif
         if (__reduce_add_sync(FULL, L.claims) > MAXLOAD) return -1;
         // ids of one sorted-unique unit list are distinct; id a itself (also the filler of idle lanes) is skipped
-        pair_probe2<S>(tbase, L, (S)b0 + 1, __umulhi(b0 * 2654435761u, NS), b0 != A.a, (S)b1 + 1,
-                       __umulhi(b1 * 2654435761u, NS), b1 != A.a, cb);
+        pair_probe2<S>(tbase, L, (S)b0 + 1, pc_slot(b0, NS), pc_step(b0, NS), b0 != A.a, (S)b1 + 1, pc_slot(b1, NS),
+                       pc_step(b1, NS), b1 != A.a, cb);
         if (!more) break;
         p = np; e = ne; j = nj; b0 = n0; b1 = n1;
       }
@@ -869,6 +953,16 @@ __device__ int pair_chunk_pass(uint32_t tbase, const PairArgs& A, int d0, int d1
   }
   pair_verify<S>(tbase, L, cb);
   const int distinct = __reduce_add_sync(FULL, L.claims);
+#ifdef CFK_PAIR_STATS
+  {  // [4] passes, [5] windows, [6] lane-iterations of the probe loop, [7] keys inserted
+    atomicAdd((unsigned long long*)A.counters + 6, (unsigned long long)L.st_iters);
+    atomicAdd((unsigned long long*)A.counters + 7, (unsigned long long)L.st_keys);
+    if (lane == 0) {
+      atomicAdd((unsigned long long*)A.counters + 4, 1ull);
+      atomicAdd((unsigned long long*)A.counters + 5, (unsigned long long)L.st_windows);
+    }
+  }
+#endif
   // emit (a, b, d0, d1) for every key whose chunk total reached min_cov
   const S cmask = ((S)1 << cb) - 1;
   constexpr int PER16 = 16 / (int)sizeof(S);
@@ -901,7 +995,7 @@ __device__ __forceinline__ int64_t warp_sum_i64(int64_t v) {
 
 template <typename S>
 __device__ void pair_source(uint32_t tbase, const PairArgs& A, int dmin, int dlim, int cb, float& ratio, int64_t& splits) {
-  constexpr int NS = PC_TBL_BYTES / (int)sizeof(S);
+  constexpr int NS = (int)PairTable<S>::NS;
   constexpr int TARGET = NS * 3 / 10;  // planned number of distinct keys per pass (hard limit NS / 2)
   const int lane = threadIdx.x & 31;
   const int64_t cnt_limit = (cb >= 32) ? (int64_t)0x7FFFFFFF : (((int64_t)1 << cb) - 1);
@@ -1147,66 +1241,69 @@ int cfk_pair_table_bytes_per_warp(void) { return PC_TBL_BYTES; }
 int cfk_pair_warps_per_block(void) { return PC_WARPS; }
 int64_t cfk_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
-int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len,
-                      const int64_t* chunk_ptr, int64_t n_reads, int64_t n_chunks, int64_t read_id_base, int k,
-                      uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1,
-                      uint64_t* t2_pairs, int64_t cap2, int64_t* counters, cfk_stream_t stream) {
+int cfk_table_init(uint64_t* table, int64_t cap, cfk_stream_t stream) {
+  if (cap < 1) return fail(CFK_ERR_INVALID, "cfk_table_init: cap < 1");
+  table_init_kernel<<<(unsigned)blocks_for(cap, 256), 256, 0, (cudaStream_t)stream>>>(table, cap);
+  CFK_CHECK_LAUNCH("table_init_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* order,
+                      int64_t n_reads, int k, uint64_t* table, int64_t cap, int64_t* counters, int32_t n_blocks,
+                      cfk_stream_t stream) {
   if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_docfreq_count: k must be in [1, 31]");
-  if (cap1 < 1 || cap1 >= (1ll << 31) || cap2 < 1)
-    return fail(CFK_ERR_INVALID, "cfk_docfreq_count: need 1 <= cap1 < 2^31 and cap2 >= 1");
-  if (n_reads < 0 || read_id_base < 0 || read_id_base + n_reads >= (1ll << 31))
-    return fail(CFK_ERR_INVALID, "cfk_docfreq_count: read ids must stay below 2^31");
-  if (n_chunks >= (1ll << 31)) return fail(CFK_ERR_INVALID, "cfk_docfreq_count: too many chunks for one launch");
-  if (n_reads == 0 || n_chunks == 0) return CFK_OK;
-  docfreq_kernel<<<(unsigned)n_chunks, DF_THREADS, 0, (cudaStream_t)stream>>>(
-      packed, read_off, read_len, chunk_ptr, n_reads, read_id_base, k, t1_keys, t1_nreads, t1_nmulti, cap1, t2_pairs,
-      cap2, counters);
+  if (cap < 1 || n_reads < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_docfreq_count: bad sizes");
+  if (n_reads == 0) return CFK_OK;
+  static bool attr_done = false;
+  const int smem = (DF_SET_SLOTS + DF_TILE_WORDS) * 4;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(docfreq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_docfreq_count: cudaFuncSetAttribute", e);
+    attr_done = true;
+  }
+  docfreq_kernel<<<(unsigned)n_blocks, DF_THREADS, smem, (cudaStream_t)stream>>>(packed, read_off, read_len, order, n_reads,
+                                                                               k, table, cap, counters);
   CFK_CHECK_LAUNCH("docfreq_kernel", 1);
   return CFK_OK;
 }
 
-int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n,
-                    uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1, int64_t* counters,
-                    cfk_stream_t stream) {
-  if (n < 0 || cap1 < 1) return fail(CFK_ERR_INVALID, "cfk_table_merge: bad sizes");
+int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n, uint64_t* table,
+                    int64_t cap, int64_t* counters, cfk_stream_t stream) {
+  if (n < 0 || cap < 1) return fail(CFK_ERR_INVALID, "cfk_table_merge: bad sizes");
   if (n == 0) return CFK_OK;
-  table_merge_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, nreads, nmulti, n, t1_keys,
-                                                                                      t1_nreads, t1_nmulti, cap1, counters);
+  table_merge_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, nreads, nmulti, n, table, cap,
+                                                                                      counters);
   CFK_CHECK_LAUNCH("table_merge_kernel", 1);
   return CFK_OK;
 }
 
-int cfk_table_select(const uint64_t* t1_keys, const uint32_t* t1_nreads, const uint32_t* t1_nmulti, int64_t cap1,
-                     uint32_t lo, uint32_t hi, uint32_t max_nonuniq, int32_t n_parts, int32_t part,
-                     uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out,
+int cfk_table_select(const uint64_t* table, int64_t cap, uint32_t lo, uint32_t hi, uint32_t max_nonuniq, int32_t n_parts,
+                     int32_t part, uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out,
                      int64_t* counters, cfk_stream_t stream) {
-  if (cap1 < 1 || max_out < 0) return fail(CFK_ERR_INVALID, "cfk_table_select: bad sizes");
+  if (cap < 1 || max_out < 0) return fail(CFK_ERR_INVALID, "cfk_table_select: bad sizes");
   if (n_parts > 0 && (part < 0 || part >= n_parts)) return fail(CFK_ERR_INVALID, "cfk_table_select: bad partition");
-  table_select_kernel<<<(unsigned)blocks_for(cap1, 256), 256, 0, (cudaStream_t)stream>>>(
-      t1_keys, t1_nreads, t1_nmulti, cap1, lo, hi, max_nonuniq, n_parts, part, out_keys, out_nreads, out_nmulti, max_out,
-      counters);
+  table_select_kernel<<<(unsigned)blocks_for(cap, 256), 256, 0, (cudaStream_t)stream>>>(
+      table, cap, lo, hi, max_nonuniq, n_parts, part, out_keys, out_nreads, out_nmulti, max_out, counters);
   CFK_CHECK_LAUNCH("table_select_kernel", 1);
   return CFK_OK;
 }
 
-int cfk_table_part_count(const uint64_t* t1_keys, int64_t cap1, int32_t n_parts, int64_t* counts,
-                         cfk_stream_t stream) {
-  if (cap1 < 1 || n_parts < 1 || n_parts > TP_MAX_PARTS)
-    return fail(CFK_ERR_INVALID, "cfk_table_part_count: need cap1 >= 1 and 1 <= n_parts <= 64");
-  const int64_t nb = blocks_for(cap1, 256 * 8);
-  table_part_count_kernel<<<(unsigned)(nb < 1 ? 1 : nb), 256, 0, (cudaStream_t)stream>>>(t1_keys, cap1, n_parts, counts);
+int cfk_table_part_count(const uint64_t* table, int64_t cap, int32_t n_parts, int64_t* counts, cfk_stream_t stream) {
+  if (cap < 1 || n_parts < 1 || n_parts > TP_MAX_PARTS)
+    return fail(CFK_ERR_INVALID, "cfk_table_part_count: need cap >= 1 and 1 <= n_parts <= 64");
+  const int64_t nb = blocks_for(cap, 256 * 8);
+  table_part_count_kernel<<<(unsigned)(nb < 1 ? 1 : nb), 256, 0, (cudaStream_t)stream>>>(table, cap, n_parts, counts);
   CFK_CHECK_LAUNCH("table_part_count_kernel", 1);
   return CFK_OK;
 }
 
-int cfk_table_part_scatter(const uint64_t* t1_keys, const uint32_t* t1_nreads, const uint32_t* t1_nmulti, int64_t cap1,
-                           int32_t n_parts, int64_t* cursors, uint64_t* out_keys, uint32_t* out_nreads,
-                           uint32_t* out_nmulti, cfk_stream_t stream) {
-  if (cap1 < 1 || n_parts < 1 || n_parts > TP_MAX_PARTS)
-    return fail(CFK_ERR_INVALID, "cfk_table_part_scatter: need cap1 >= 1 and 1 <= n_parts <= 64");
-  const int64_t nb = blocks_for(cap1, 256 * 8);
-  table_part_scatter_kernel<<<(unsigned)(nb < 1 ? 1 : nb), 256, 0, (cudaStream_t)stream>>>(
-      t1_keys, t1_nreads, t1_nmulti, cap1, n_parts, cursors, out_keys, out_nreads, out_nmulti);
+int cfk_table_part_scatter(const uint64_t* table, int64_t cap, int32_t n_parts, int64_t* cursors, uint64_t* out_keys,
+                           uint32_t* out_nreads, uint32_t* out_nmulti, cfk_stream_t stream) {
+  if (cap < 1 || n_parts < 1 || n_parts > TP_MAX_PARTS)
+    return fail(CFK_ERR_INVALID, "cfk_table_part_scatter: need cap >= 1 and 1 <= n_parts <= 64");
+  const int64_t nb = blocks_for(cap, 256 * 8);
+  table_part_scatter_kernel<<<(unsigned)(nb < 1 ? 1 : nb), 256, 0, (cudaStream_t)stream>>>(table, cap, n_parts, cursors,
+                                                                                           out_keys, out_nreads, out_nmulti);
   CFK_CHECK_LAUNCH("table_part_scatter_kernel", 1);
   return CFK_OK;
 }

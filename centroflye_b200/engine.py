@@ -20,7 +20,6 @@ from . import _lib
 from ._lib import CfkError
 from .encode import check_k
 
-DOCFREQ_CHUNK = 2048
 U32_MAX = 0xFFFFFFFF
 
 
@@ -36,9 +35,8 @@ class DeviceReads:
     packed: object      # int32[n_words]
     read_off: object    # int64[R]
     read_len: object    # int64[R]
-    chunk_ptr: object   # int64[R+1]
+    order: object       # int32[R]  read indices, longest first (work order of the stage-A kernel)
     n_reads: int
-    n_chunks: int
     n_bases: int
     h2d_bytes: int
 
@@ -56,9 +54,7 @@ class DeviceUnits:
 
 @dataclass
 class DocFreqTable:
-    keys: object        # int64[cap]  (uint64 bit patterns, -1 = empty)
-    nreads: object      # int32[cap]
-    nmulti: object      # int32[cap]
+    slots: object       # int64[2 * cap]: per slot (key as uint64 bits, -1 = empty ; n_reads | n_multi << 32)
     cap: int
 
 
@@ -100,7 +96,7 @@ class Engine:
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.cand_hint = 1 << 20
         self.edge_hint = 1 << 20
-        self.table_load = 0.5
+        self.table_load = 0.6  # distinct k-mers <= occurrences, so the stage-A table is at most this full
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
 
     # ---- plumbing ---------------------------------------------------------------------------
@@ -152,15 +148,13 @@ class Engine:
 
     # ---- uploads ----------------------------------------------------------------------------
     def upload_reads(self, batch, k):
-        """ReadBatch -> device; chunk_ptr is the block map of the stage-A kernel."""
-        nk = np.maximum(batch.read_len - k + 1, 0)
-        chunk_ptr = np.zeros(batch.n_reads + 1, dtype=np.int64)
-        np.cumsum((nk + DOCFREQ_CHUNK - 1) // DOCFREQ_CHUNK, out=chunk_ptr[1:])
+        """ReadBatch -> device (pinned staging, async copies)."""
+        order = np.argsort(-batch.read_len, kind="stable").astype(np.int32)
         packed = batch.packed.view(np.int32)
-        h2d = packed.nbytes + batch.read_off.nbytes + batch.read_len.nbytes + chunk_ptr.nbytes
+        h2d = packed.nbytes + batch.read_off.nbytes + batch.read_len.nbytes + order.nbytes
         return DeviceReads(packed=self._to_dev(packed), read_off=self._to_dev(batch.read_off),
-                           read_len=self._to_dev(batch.read_len), chunk_ptr=self._to_dev(chunk_ptr),
-                           n_reads=batch.n_reads, n_chunks=int(chunk_ptr[-1]), n_bases=batch.n_bases, h2d_bytes=h2d)
+                           read_len=self._to_dev(batch.read_len), order=self._to_dev(order),
+                           n_reads=batch.n_reads, n_bases=batch.n_bases, h2d_bytes=h2d)
 
     def upload_units(self, units, k):
         nk = np.maximum(units.unit_len.astype(np.int64) - k + 1, 0)
@@ -177,41 +171,35 @@ class Engine:
 
     # ---- stage A ----------------------------------------------------------------------------
     def new_table(self, cap):
-        t = self.torch
-        return DocFreqTable(keys=t.full((cap,), -1, dtype=t.int64, device=self.device),
-                            nreads=self._zeros(cap, t.int32), nmulti=self._zeros(cap, t.int32), cap=int(cap))
+        slots = self._empty(2 * int(cap), self.torch.int64)
+        _lib.call("cfk_table_init", self._p(slots), int(cap), self._stream())
+        return DocFreqTable(slots=slots, cap=int(cap))
 
-    def count_docfreq(self, reads, k, read_id_base=0, n_kmers_hint=None):
-        """One pass over all reads -> DocFreqTable (grown and recounted if a table fills up)."""
+    def count_docfreq(self, reads, k, n_kmers_hint=None):
+        """One pass over all reads -> DocFreqTable (grown and recounted if the table fills up)."""
         k = check_k(k)
-        t = self.torch
         total_k = n_kmers_hint if n_kmers_hint is not None else max(reads.n_bases - reads.n_reads * (k - 1), 0)
-        cap1 = max(1024, int(total_k / self.table_load) + 1)
-        cap2 = cap1
+        cap = max(1024, int(total_k / self.table_load) + 1)
         while True:
-            table = self.new_table(cap1)
-            pairs = t.full((cap2,), -1, dtype=t.int64, device=self.device)
+            table = self.new_table(cap)
             counters = self._counters()
             with self._stage("docfreq"):
                 _lib.call("cfk_docfreq_count", self._p(reads.packed), self._p(reads.read_off),
-                          self._p(reads.read_len), self._p(reads.chunk_ptr), reads.n_reads, reads.n_chunks,
-                          read_id_base, k, self._p(table.keys), self._p(table.nreads), self._p(table.nmulti), cap1,
-                          self._p(pairs), cap2, self._p(counters), self._stream())
+                          self._p(reads.read_len), self._p(reads.order), reads.n_reads, k, self._p(table.slots), cap,
+                          self._p(counters), self.n_sms, self._stream())
             c = counters.cpu()
-            del pairs
-            if int(c[0]) == 0 and int(c[1]) == 0:
+            if int(c[1]):
+                raise CfkError("stage A: per-read k-mer set overflowed (internal error)")
+            if int(c[0]) == 0:
                 return table
-            cap1 *= 2 if int(c[0]) else 1
-            cap2 *= 2 if int(c[1]) else 1
-            if cap1 >= (1 << 31):
-                raise CfkError("stage-A table would exceed 2^31 slots; split the read set into batches")
+            cap *= 2
 
     def table_select(self, table, lo, hi, max_nonuniq, with_counts=False, n_parts=0, part=0):
         """Compacted (keys[, n_reads, n_multi]) of slots inside the band, unordered."""
         t = self.torch
         counters = self._counters()
-        args = (self._p(table.keys), self._p(table.nreads), self._p(table.nmulti), table.cap,
-                int(lo), int(min(hi, U32_MAX)), int(min(max_nonuniq, U32_MAX)), n_parts, part)
+        args = (self._p(table.slots), table.cap, int(lo), int(min(hi, U32_MAX)), int(min(max_nonuniq, U32_MAX)),
+                n_parts, part)
         _lib.call("cfk_table_select", *args, None, None, None, 0, self._p(counters), self._stream())
         n = int(counters.cpu()[0])
         keys = self._empty(n, t.int64)
@@ -227,7 +215,7 @@ class Engine:
     def part_count(self, table, n_parts):
         """int64[n_parts] (device): occupied slots per hash partition (owner = mix64(key ^ golden) % n_parts)."""
         counts = self._zeros(n_parts, self.torch.int64)
-        _lib.call("cfk_table_part_count", self._p(table.keys), table.cap, n_parts, self._p(counts), self._stream())
+        _lib.call("cfk_table_part_count", self._p(table.slots), table.cap, n_parts, self._p(counts), self._stream())
         return counts
 
     def part_scatter(self, table, n_parts, counts):
@@ -236,16 +224,14 @@ class Engine:
         total = int(counts.sum().item())
         cursors = (t.cumsum(counts, 0) - counts).contiguous()
         keys, nreads, nmulti = self._empty(total, t.int64), self._empty(total, t.int32), self._empty(total, t.int32)
-        _lib.call("cfk_table_part_scatter", self._p(table.keys), self._p(table.nreads), self._p(table.nmulti),
-                  table.cap, n_parts, self._p(cursors), self._p(keys), self._p(nreads), self._p(nmulti),
-                  self._stream())
+        _lib.call("cfk_table_part_scatter", self._p(table.slots), table.cap, n_parts, self._p(cursors), self._p(keys),
+                  self._p(nreads), self._p(nmulti), self._stream())
         return keys[:total], nreads[:total], nmulti[:total]
 
     def merge_into(self, table, keys, nreads, nmulti):
         counters = self._counters()
         _lib.call("cfk_table_merge", self._p(keys), self._p(nreads), self._p(nmulti), int(keys.numel()),
-                  self._p(table.keys), self._p(table.nreads), self._p(table.nmulti), table.cap,
-                  self._p(counters), self._stream())
+                  self._p(table.slots), table.cap, self._p(counters), self._stream())
         if int(counters.cpu()[0]):
             raise CfkError("owner-side table full during merge")
 
@@ -367,6 +353,7 @@ class Engine:
                           a_stride, int(min_d), int(max_d), min_cov_u, self._p(cand), max_cand, self._p(counters),
                           self.n_sms, self._stream())
             c = counters.cpu()
+            self.last_pair_counters = [int(x) for x in c.tolist()]
             n_cand = int(c[0])
             if n_cand <= max_cand:
                 break

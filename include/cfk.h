@@ -35,7 +35,7 @@ extern "C" {
 #define CFK_ERR_CUDA (-2)
 
 #define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
-#define CFK_DOCFREQ_CHUNK 2048 /* k-mer start positions handled by one thread block */
+#define CFK_DOCFREQ_SET_SLOTS 49152 /* 32-bit slots of the per-read k-mer set in shared memory (192 KB) */
 #ifndef CFK_PAIR_WARPS
 #define CFK_PAIR_WARPS 20         /* warps per block of the stage-C kernel (one block per SM) */
 #endif
@@ -54,25 +54,29 @@ int cfk_pair_warps_per_block(void);
 int64_t cfk_launch_count(void);
 
 /* ---- stage A: document-frequency k-mer count --------------------------------------------
- * Replaces get_kmer_freqs_from_ncrf_report, distance_based_kmer_recruitment.py:39-63.
- * For every read r (global id read_id_base + r) and every k-mer of its gap-free row:
- *   slot = find-or-insert(t1_keys, kmer); first (slot, read) sighting -> t1_nreads[slot]++,
- *   second sighting in the same read -> t1_nmulti[slot]++ (once per read).
- * t1_keys / t2_pairs must be pre-filled with CFK_EMPTY_KEY, t1_nreads / t1_nmulti with 0;
- * calling again with more reads (distinct read ids) accumulates.  chunk_ptr[r] = number of
- * CFK_DOCFREQ_CHUNK-sized chunks in reads < r (chunk_ptr[n_reads] = grid size).
- * counters[0] != 0: t1 full; counters[1] != 0: t2 full (results invalid, grow and retry).
+ * The table is open addressing over `cap` 16-byte slots { uint64 key ; uint32 n_reads ;
+ * uint32 n_multi } stored as 2 x uint64 per slot (counts in the second word, n_reads low);
+ * cfk_table_init writes (CFK_EMPTY_KEY, 0) into every slot.
+ *
+ * cfk_docfreq_count replaces get_kmer_freqs_from_ncrf_report,
+ * distance_based_kmer_recruitment.py:39-63: for every read r and every DISTINCT k-mer of its
+ * gap-free row n_reads[kmer] += 1, and n_multi[kmer] += 1 if the k-mer occurs in r more than
+ * once (the closed form of the sequential update at :55-62).  The per-read
+ * de-duplication (the reference's read_freq dict, :50-53) is done in shared memory by one
+ * persistent thread block per read; `order` lists the read indices longest first (load
+ * balance), n_blocks = number of SMs.  Calling again with more reads accumulates.
+ * counters (zeroed by the caller): [0] != 0: table full (results invalid, grow and retry),
+ * [1] != 0: internal set overflow (a bug), [2] read cursor.
  */
-int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len,
-                      const int64_t* chunk_ptr, int64_t n_reads, int64_t n_chunks, int64_t read_id_base, int k,
-                      uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1,
-                      uint64_t* t2_pairs, int64_t cap2, int64_t* counters, cfk_stream_t stream);
+int cfk_table_init(uint64_t* table, int64_t cap, cfk_stream_t stream);
+int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* order,
+                      int64_t n_reads, int k, uint64_t* table, int64_t cap, int64_t* counters, int32_t n_blocks,
+                      cfk_stream_t stream);
 
 /* Merge (key, n_reads, n_multi) records counted elsewhere (another GPU's shard) into a table:
  * the owner-side half of the multi-GPU all-to-all.  counters[0] != 0: full. */
-int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n,
-                    uint64_t* t1_keys, uint32_t* t1_nreads, uint32_t* t1_nmulti, int64_t cap1,
-                    int64_t* counters, cfk_stream_t stream);
+int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n, uint64_t* table,
+                    int64_t cap, int64_t* counters, cfk_stream_t stream);
 
 /* ---- band filter -------------------------------------------------------------------------
  * Replaces the dict comprehension of get_rare_kmers, distance_based_kmer_recruitment.py:77-79,
@@ -82,9 +86,8 @@ int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t
  * taken (hash partition for the multi-GPU exchange).  counters[0] (zeroed by the caller)
  * receives the number of matches even beyond max_out; nothing is written past max_out.
  */
-int cfk_table_select(const uint64_t* t1_keys, const uint32_t* t1_nreads, const uint32_t* t1_nmulti, int64_t cap1,
-                     uint32_t lo, uint32_t hi, uint32_t max_nonuniq, int32_t n_parts, int32_t part,
-                     uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out,
+int cfk_table_select(const uint64_t* table, int64_t cap, uint32_t lo, uint32_t hi, uint32_t max_nonuniq, int32_t n_parts,
+                     int32_t part, uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out,
                      int64_t* counters, cfk_stream_t stream);
 
 /* Hash partition of a whole table for the multi-GPU exchange: every occupied
@@ -94,10 +97,8 @@ int cfk_table_select(const uint64_t* t1_keys, const uint32_t* t1_nreads, const u
  * partition p occupies [cursors[p], cursors[p] + count[p]) of the output arrays -- cursors
  * holds the exclusive prefix of the counts on entry and the end offsets on return.  This is the
  * send buffer layout of the NCCL all-to-all; the receiver feeds cfk_table_merge. */
-int cfk_table_part_count(const uint64_t* t1_keys, int64_t cap1, int32_t n_parts, int64_t* counts,
-                         cfk_stream_t stream);
-int cfk_table_part_scatter(const uint64_t* t1_keys, const uint32_t* t1_nreads, const uint32_t* t1_nmulti,
-                           int64_t cap1, int32_t n_parts, int64_t* cursors, uint64_t* out_keys,
+int cfk_table_part_count(const uint64_t* table, int64_t cap, int32_t n_parts, int64_t* counts, cfk_stream_t stream);
+int cfk_table_part_scatter(const uint64_t* table, int64_t cap, int32_t n_parts, int64_t* cursors, uint64_t* out_keys,
                            uint32_t* out_nreads, uint32_t* out_nmulti, cfk_stream_t stream);
 
 /* In-place ascending sort of n uint64 keys (bitonic network, shared-memory tiles).  The rank

@@ -46,7 +46,7 @@ def test_argument_validation_without_gpu(lib_path):
     from centroflye_b200 import _lib
     lib = _lib.load()
     with pytest.raises(_lib.CfkError, match="k must be"):
-        _lib.call("cfk_docfreq_count", None, None, None, None, 1, 1, 0, 32, None, None, None, 10, None, 10, None, None)
+        _lib.call("cfk_docfreq_count", None, None, None, None, 1, 32, None, 10, None, 1, None)
     with pytest.raises(_lib.CfkError, match="min_d"):
         _lib.call("cfk_pair_candidates", None, None, None, None, None, None, 5, 10, 0, 10, 1, -1, 5, 1, None, 0, None, 1,
                   None)

@@ -152,11 +152,9 @@ def test_table_select_partitions_cover_table(eng):
              for o, n in zip(batch.read_off, batch.read_len)]
     half = len(codes) // 2
     t_sum = eng.new_table(table.cap)
-    base = 0
     for part_codes in (codes[:half], codes[half:]):
         b = pack_reads(part_codes, [f"r{i}" for i in range(len(part_codes))])
-        t_part = eng.count_docfreq(eng.upload_reads(b, 17), 17, read_id_base=base)
-        base += len(part_codes)
+        t_part = eng.count_docfreq(eng.upload_reads(b, 17), 17)
         eng.merge_into(t_sum, *eng.table_select(t_part, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True))
     k2, r2, m2 = eng.table_select(t_sum, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)
     assert dict(zip(k2.cpu().numpy().tolist(), zip(r2.cpu().numpy().tolist(), m2.cpu().numpy().tolist()))) == whole
