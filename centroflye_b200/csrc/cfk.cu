@@ -1074,6 +1074,58 @@ __device__ void pair_source(uint32_t tbase, const PairArgs& A, int dmin, int dli
   }
 }
 
+// Per-source prologue shared by both stage-C kernels.  Adds the reference's number of `+= 1` executions for
+// this source (dbkr.py:126) to incr_total, in closed form: every id of every unit g + d, d in [dmin, max_d],
+// minus the occurrences of a itself in them.  Returns the largest distance worth streaming (exact pruning:
+// cnt[d][a][b] >= min_cov needs >= min_cov occurrences whose read still has a unit g + d), dmin - 1 if none.
+__device__ int source_scope(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ unit_last,
+                            const uint32_t* __restrict__ occ_a, int64_t m, int dmin, int max_d, uint32_t min_cov,
+                            int64_t& incr_total) {
+  const int lane = threadIdx.x & 31;
+  int64_t entries = 0, self = 0, maxrem = 0;
+  for (int64_t t0 = 0; t0 < m; t0 += 32) {
+    const int64_t t = t0 + lane;
+    if (t < m) {
+      const int64_t g = (int64_t)__ldg(occ_a + t);
+      const int64_t last = (int64_t)__ldg(unit_last + g);
+      const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, last);
+      if (lo <= hi) {
+        entries += __ldg(unit_ptr + hi + 1) - __ldg(unit_ptr + lo);
+        self += lower_bound_u32(occ_a, t + 1, m, hi + 1) - lower_bound_u32(occ_a, t + 1, m, lo);
+      }
+      maxrem = max(maxrem, last - g);
+    }
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    entries += __shfl_xor_sync(FULL, entries, o);
+    self += __shfl_xor_sync(FULL, self, o);
+    maxrem = max(maxrem, __shfl_xor_sync(FULL, maxrem, o));
+  }
+  incr_total += entries - self;
+  int dlim = (int)min((int64_t)max_d, maxrem);
+  if (min_cov > 1) {
+    if ((uint64_t)m < (uint64_t)min_cov) return dmin - 1;
+    // largest d with at least min_cov occurrences whose read still has a unit g + d
+    int lo_d = dmin - 1, hi_d = dlim;  // invariant: count(lo_d) >= min_cov or lo_d == dmin - 1
+    while (lo_d < hi_d) {
+      const int mid = (lo_d + hi_d + 1) >> 1;
+      int64_t c = 0;
+      for (int64_t t0 = 0; t0 < m; t0 += 32) {
+        const int64_t t = t0 + lane;
+        bool ge = false;
+        if (t < m) {
+          const int64_t g = (int64_t)__ldg(occ_a + t);
+          ge = (int64_t)__ldg(unit_last + g) - g >= mid;
+        }
+        c += __popc(__ballot_sync(FULL, ge));
+      }
+      if (c >= (int64_t)min_cov) lo_d = mid; else hi_d = mid - 1;
+    }
+    dlim = lo_d;
+  }
+  return dlim;
+}
+
 __global__ void __launch_bounds__(PC_WARPS * 32, 1)
 pair_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
                        const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
@@ -1098,49 +1150,7 @@ pair_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __r
     const int64_t o0 = occ_ptr[a], m = occ_ptr[a + 1] - o0;
     if (m == 0) continue;
     const uint32_t* occ_a = occ + o0;
-    // the reference's number of `+= 1` executions for this source (dbkr.py:126), in closed form:
-    // every id of every unit g + d, d in [dmin, dmax], minus the occurrences of a itself in them
-    int64_t entries = 0, self = 0, maxrem = 0;
-    for (int64_t t0 = 0; t0 < m; t0 += 32) {
-      const int64_t t = t0 + lane;
-      if (t < m) {
-        const int64_t g = (int64_t)__ldg(occ_a + t);
-        const int64_t last = (int64_t)__ldg(unit_last + g);
-        const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, last);
-        if (lo <= hi) {
-          entries += __ldg(unit_ptr + hi + 1) - __ldg(unit_ptr + lo);
-          self += lower_bound_u32(occ_a, t + 1, m, hi + 1) - lower_bound_u32(occ_a, t + 1, m, lo);
-        }
-        maxrem = max(maxrem, last - g);
-      }
-    }
-    for (int o = 16; o >= 1; o >>= 1) {
-      entries += __shfl_xor_sync(FULL, entries, o);
-      self += __shfl_xor_sync(FULL, self, o);
-      maxrem = max(maxrem, __shfl_xor_sync(FULL, maxrem, o));
-    }
-    incr_total += entries - self;
-    int dlim = (int)min((int64_t)max_d, maxrem);
-    if (min_cov > 1) {
-      if ((uint64_t)m < (uint64_t)min_cov) continue;
-      // largest d with at least min_cov occurrences whose read still has a unit g + d
-      int lo_d = dmin - 1, hi_d = dlim;  // invariant: count(lo_d) >= min_cov or lo_d == dmin - 1
-      while (lo_d < hi_d) {
-        const int mid = (lo_d + hi_d + 1) >> 1;
-        int64_t c = 0;
-        for (int64_t t0 = 0; t0 < m; t0 += 32) {
-          const int64_t t = t0 + lane;
-          bool ge = false;
-          if (t < m) {
-            const int64_t g = (int64_t)__ldg(occ_a + t);
-            ge = (int64_t)__ldg(unit_last + g) - g >= mid;
-          }
-          c += __popc(__ballot_sync(FULL, ge));
-        }
-        if (c >= (int64_t)min_cov) lo_d = mid; else hi_d = mid - 1;
-      }
-      dlim = lo_d;
-    }
+    const int dlim = source_scope(unit_ptr, unit_last, occ_a, m, dmin, max_d, min_cov, incr_total);
     if (dlim < dmin) continue;
     PairArgs A{unit_ptr, ids, unit_last, occ_a, usplit, m, n_kmers, a, min_cov, cand, max_cand, counters};
     const int mb = 64 - __clzll((unsigned long long)m);  // a single-distance count never exceeds m
@@ -1148,6 +1158,315 @@ pair_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __r
       pair_source<uint32_t>(tbase, A, dmin, dlim, 32 - kb, ratio, splits);
     else
       pair_source<uint64_t>(tbase, A, dmin, dlim, 32, ratio, splits);
+  }
+  if (lane == 0) {
+    if (incr_total) atomicAdd((unsigned long long*)(counters + 2), (unsigned long long)incr_total);
+    if (splits) atomicAdd((unsigned long long*)(counters + 3), (unsigned long long)splits);
+  }
+}
+
+// ============================================================================================
+// Stage C, sketch form (the default for 3 <= min_cov <= 255).
+//
+// The exact tables above spend ~6 instructions and a probe chain per pair increment, although
+// > 99 % of the increments go to counters that never reach min_cov.  Here one pass over the
+// distances [d0, d0 + nd) of a source a only answers "can b reach min_cov?":
+//
+//   level 1  a warp-private array of 2^SK_BITS saturating BYTE counters indexed by a hash of b.
+//            counter[h] counts the units of the pass holding some id with hash h, which is
+//            >= the number of units holding b itself: an upper bound of sum_d cnt[d][a][b].
+//            The hash and a "same hash as an earlier id of this unit" flag are precomputed per
+//            cloud entry (codes[], 2 bytes per entry, cfk_sketch_codes): flagged entries do not
+//            store, so the lanes of one step always write DISTINCT bytes -- plain ld/st, no
+//            atomics, no keys, no probe chains.
+//   level 2  an entry whose counter is already >= min_cov - 1 is "hot": its position is queued
+//            and, 32 at a time, the real id is fetched and put into a small exact hash SET.
+//            Every b with sum_d cnt[d][a][b] >= min_cov is hot at its min_cov-th unit at the
+//            latest, so the set is a superset of the true candidates (hash collisions only add
+//            members); the set is emitted as (a, b, d0, d1) once the pass is complete.
+//
+// cfk_pair_join then computes the exact per-distance counts of those pairs, exactly as for the
+// exact tables.  A pass whose set overflows is abandoned before anything is emitted and redone
+// over fewer distances / a narrower id range.
+// ============================================================================================
+constexpr int SK_BITS = CFK_SKETCH_BITS;
+constexpr int SK_TBL_BYTES = 1 << SK_BITS;
+constexpr uint32_t SK_OFF_MASK = (uint32_t)SK_TBL_BYTES - 1u;
+constexpr uint32_t SK_DUP = 0x8000u;
+constexpr uint32_t SK_INV = 0xFFFFFFFFu;
+constexpr int SK_L2_SLOTS = 256;   // level-2 set, u32 slots holding b + 1
+constexpr int SK_L2_MAX = 192;
+constexpr int SK_Q_SLOTS = 256;    // queue of hot positions
+constexpr int SK_WINDOW = 128;     // cloud entries per step (4 per lane)
+constexpr int SK_WARP_BYTES = SK_TBL_BYTES + SK_L2_SLOTS * 4 + SK_Q_SLOTS * 4;
+constexpr int SK_WARPS_FIT = (227 * 1024 - 256) / SK_WARP_BYTES;
+constexpr int SK_WARPS = SK_WARPS_FIT > 32 ? 32 : SK_WARPS_FIT;
+constexpr uint32_t SK_CAP = (uint32_t)SK_TBL_BYTES / CFK_SKETCH_LOAD_DIV;  // planned cloud entries per pass
+constexpr int SK_ND_MAX = 16;
+static_assert(SK_BITS >= 10 && SK_BITS <= 15, "codes are 16 bit: hash in the low bits, bit 15 = duplicate flag");
+static_assert(SK_WARPS >= 1, "sketch does not fit shared memory");
+
+__device__ __forceinline__ uint32_t sk_hash(uint32_t id) { return (id * 0x9E3779B1u) >> (32 - SK_BITS); }
+
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t atom_cas_shared(uint32_t a, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+
+// codes[p] = hash of ids[p] | SK_DUP if an earlier-served id of the same unit has the same hash.  Warp per unit.
+__global__ void __launch_bounds__(256) sketch_codes_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
+                                                           int64_t n_units, uint16_t* __restrict__ codes) {
+  __shared__ uint32_t bm[8][SK_TBL_BYTES / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t u = (int64_t)blockIdx.x * 8 + warp;
+  if (u >= n_units) return;
+  const int64_t b = unit_ptr[u], e = unit_ptr[u + 1];
+  if (b == e) return;
+  for (int i = lane; i < SK_TBL_BYTES / 32; i += 32) bm[warp][i] = 0;
+  __syncwarp();
+  for (int64_t p = b + lane; p < e; p += 32) {
+    const uint32_t h = sk_hash(ids[p]);
+    const uint32_t old = atomicOr(&bm[warp][h >> 5], 1u << (h & 31u));
+    codes[p] = (uint16_t)(h | (((old >> (h & 31u)) & 1u) ? SK_DUP : 0u));
+  }
+}
+
+struct SketchArgs {
+  const int64_t* __restrict__ unit_ptr;
+  const uint32_t* __restrict__ ids;
+  const uint16_t* __restrict__ codes;
+  const uint32_t* __restrict__ unit_last;
+  const uint32_t* __restrict__ occ_a;
+  int64_t m;
+  int64_t n_kmers;
+  uint32_t a;
+  uint32_t thr;  // min_cov - 1, 2 <= thr <= 254
+  uint4* cand;
+  int64_t max_cand;
+  int64_t* counters;
+};
+
+// the four codes of this lane in the window starting at position p of a unit list ending at e
+__device__ __forceinline__ void sk_load(const SketchArgs& A, uint32_t p, uint32_t e, int lane, uint32_t (&c)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t q = p + (uint32_t)lane + 32u * i;
+    c[i] = (q < e) ? (uint32_t)__ldg(A.codes + q) : SK_INV;
+  }
+}
+
+// queued hot positions -> level-2 set.  Returns false if the set overflowed.
+__device__ bool sk_drain(uint32_t l2base, uint32_t qbase, const SketchArgs& A, int qn, int64_t lo_id, int64_t hi_id,
+                         int& claims) {
+  const int lane = threadIdx.x & 31;
+  bool ovf = false;
+  __syncwarp();
+  for (int base = 0; base < qn; base += 32) {
+    const int idx = base + lane;
+    if (idx < qn) {
+      const uint32_t pos = lds<uint32_t>(qbase + (uint32_t)idx * 4u);
+      const uint32_t b = __ldg(A.ids + pos);
+      if (b != A.a && (int64_t)b >= lo_id && (int64_t)b < hi_id) {
+        const uint32_t key = b + 1u;
+        uint32_t slot = (b * 0x85EBCA77u) >> 24;
+        static_assert(SK_L2_SLOTS == 256, "slot hash takes the top 8 bits");
+        int probes = 0;
+        for (; probes < SK_L2_SLOTS; ++probes) {
+          const uint32_t old = atom_cas_shared(l2base + slot * 4u, 0u, key);
+          if (old == 0u) { ++claims; break; }
+          if (old == key) break;
+          slot = (slot + 1u) & (uint32_t)(SK_L2_SLOTS - 1);
+        }
+        if (probes == SK_L2_SLOTS) ovf = true;
+      }
+    }
+  }
+  __syncwarp();
+  const int total = __reduce_add_sync(FULL, claims);
+  return !(__any_sync(FULL, ovf) || total > SK_L2_MAX);
+}
+
+// One pass: distances d0 .. d0 + nd - 1, hot ids restricted to [lo_id, hi_id).  Returns the number
+// of candidates emitted, or -1 if the level-2 set overflowed (nothing emitted).
+__device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, int64_t lo_id, int64_t hi_id) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  const uint32_t l2base = tbase + SK_TBL_BYTES, qbase = l2base + SK_L2_SLOTS * 4;
+#pragma unroll 4
+  for (int i = lane; i < (SK_TBL_BYTES + SK_L2_SLOTS * 4) / 16; i += 32) sts128(tbase + (uint32_t)i * 16u, make_uint4(0, 0, 0, 0));
+  __syncwarp();
+  int qn = 0, claims = 0;
+  const int64_t n_items = A.m * (int64_t)nd;
+  for (int64_t i0 = 0; i0 < n_items; i0 += 32) {
+    const int64_t it = i0 + lane;
+    uint32_t up = 0, ue = 0;  // this lane's unit list [up, ue)
+    if (it < n_items) {
+      const int64_t t = (nd == 1) ? it : it / nd;
+      const int64_t g = (int64_t)__ldg(A.occ_a + t);
+      const int64_t u = g + d0 + (it - t * nd);
+      if (u <= (int64_t)__ldg(A.unit_last + g)) {
+        up = (uint32_t)__ldg(A.unit_ptr + u);
+        ue = (uint32_t)__ldg(A.unit_ptr + u + 1);
+      }
+    }
+    unsigned rest = __ballot_sync(FULL, ue > up);
+    if (!rest) continue;
+    int src = __ffs(rest) - 1;
+    rest &= rest - 1;
+    uint32_t p = __shfl_sync(FULL, up, src), e = __shfl_sync(FULL, ue, src);
+    uint32_t c[4], n[4];
+    sk_load(A, p, e, lane, c);
+    for (;;) {
+      // the next window (rest of this unit, else the next unit of the group): its codes fly during this step
+      uint32_t np = p + SK_WINDOW, ne = e;
+      bool more = true;
+      if (np >= ne) {
+        if (rest) {
+          src = __ffs(rest) - 1;
+          rest &= rest - 1;
+          np = __shfl_sync(FULL, up, src);
+          ne = __shfl_sync(FULL, ue, src);
+        } else {
+          more = false;
+        }
+      }
+      if (more) sk_load(A, np, ne, lane, n);
+      // level 1: non-flagged entries of one unit have distinct hashes, so all stores of a step hit distinct bytes
+      uint32_t old[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) old[i] = (c[i] != SK_INV) ? lds_u8(tbase + (c[i] & SK_OFF_MASK)) : 0u;
+      uint32_t hot = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (c[i] != SK_INV) {
+          if (old[i] >= A.thr) hot |= 1u << i;
+          if (!(c[i] & SK_DUP)) sts_u8(tbase + (c[i] & SK_OFF_MASK), old[i] + (old[i] != 255u));
+        }
+      }
+      if (__any_sync(FULL, hot != 0)) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool h = (hot >> i) & 1u;
+          const unsigned bal = __ballot_sync(FULL, h);
+          if (h) sts(qbase + (uint32_t)(qn + __popc(bal & lt)) * 4u, p + (uint32_t)lane + 32u * i);
+          qn += __popc(bal);
+        }
+        if (qn > SK_Q_SLOTS - SK_WINDOW) {
+          if (!sk_drain(l2base, qbase, A, qn, lo_id, hi_id, claims)) return -1;
+          qn = 0;
+        }
+      }
+      __syncwarp();
+      if (!more) break;
+      p = np; e = ne;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[i] = n[i];
+    }
+  }
+  if (!sk_drain(l2base, qbase, A, qn, lo_id, hi_id, claims)) return -1;
+  // emit the set
+  int emitted = 0;
+  for (int i = lane; i < SK_L2_SLOTS / 4; i += 32) {
+    const uint4 q = lds128(l2base + (uint32_t)i * 16u);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    if (__any_sync(FULL, (q.x | q.y | q.z | q.w) != 0u)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool take = w[j] != 0u;
+        const int64_t pos = warp_append(take, A.counters);
+        if (take && pos < A.max_cand) A.cand[pos] = make_uint4(A.a, w[j] - 1u, (uint32_t)d0, (uint32_t)(d0 + nd - 1));
+        emitted += take;
+      }
+    }
+  }
+  __syncwarp();
+  return emitted;
+}
+
+__device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int dlim, int64_t& splits) {
+  const int lane = threadIdx.x & 31;
+  int d0 = dmin;
+  int nd_force = SK_ND_MAX;
+  while (d0 <= dlim) {
+    // plan: extend the pass one distance at a time (4 looked up per round) while the cloud entries fit SK_CAP
+    const int nd_max = min(nd_force, dlim - d0 + 1);
+    int nd = 0;
+    uint32_t tot = 0, first = 0;
+    bool stop = false;
+    for (int jb = 0; jb < nd_max && !stop; jb += 4) {
+      uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+      for (int64_t t0 = 0; t0 < A.m; t0 += 32) {
+        const int64_t t = t0 + lane;
+        if (t < A.m) {
+          const int64_t g = (int64_t)__ldg(A.occ_a + t);
+          const int64_t lim = (int64_t)__ldg(A.unit_last + g) + 1;
+          const int64_t u = g + d0 + jb;
+          const uint32_t p0 = (uint32_t)__ldg(A.unit_ptr + min(u, lim)), p1 = (uint32_t)__ldg(A.unit_ptr + min(u + 1, lim)),
+                         p2 = (uint32_t)__ldg(A.unit_ptr + min(u + 2, lim)), p3 = (uint32_t)__ldg(A.unit_ptr + min(u + 3, lim)),
+                         p4 = (uint32_t)__ldg(A.unit_ptr + min(u + 4, lim));
+          c0 += p1 - p0; c1 += p2 - p1; c2 += p3 - p2; c3 += p4 - p3;
+        }
+      }
+      const uint32_t c[4] = {__reduce_add_sync(FULL, c0), __reduce_add_sync(FULL, c1), __reduce_add_sync(FULL, c2),
+                             __reduce_add_sync(FULL, c3)};
+      if (jb == 0) first = c[0];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (stop || jb + k >= nd_max) { stop = true; continue; }
+        if (c[k] <= SK_CAP && tot <= SK_CAP - c[k]) { tot += c[k]; ++nd; } else stop = true;
+      }
+    }
+    if (nd < 1) { nd = 1; tot = first; }
+    if (tot == 0) { d0 += nd; nd_force = SK_ND_MAX; continue; }
+    bool redo = false;
+    int64_t lo_id = 0, width = A.n_kmers;
+    while (lo_id < A.n_kmers) {
+      const int64_t hi_id = min(A.n_kmers, lo_id + width);
+      if (sketch_pass(tbase, A, d0, nd, lo_id, hi_id) < 0) {  // level-2 set overflow: fewer distances, then narrower id ranges
+        ++splits;
+        if (nd > 1) { nd_force = nd >> 1; redo = true; break; }
+        width = max((int64_t)1, (hi_id - lo_id) >> 1);
+        continue;
+      }
+      lo_id = hi_id;
+    }
+    if (redo) continue;
+    d0 += nd;
+    nd_force = SK_ND_MAX;
+  }
+}
+
+__global__ void __launch_bounds__(SK_WARPS * 32, 1)
+pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids, const uint16_t* __restrict__ codes,
+                   const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
+                   const uint32_t* __restrict__ occ, int64_t n_kmers, int64_t a_begin, int64_t a_end, int32_t a_stride,
+                   int32_t min_d, int32_t max_d, uint32_t min_cov, uint4* cand, int64_t max_cand, int64_t* counters) {
+  extern __shared__ __align__(16) unsigned char pc_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(pc_smem) + (uint32_t)warp * SK_WARP_BYTES;
+  const int dmin = max(min_d, 1);
+  int64_t incr_total = 0, splits = 0;
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd((unsigned long long*)(counters + 1), 1ull);
+    item = __shfl_sync(FULL, item, 0);
+    const int64_t a64 = a_begin + (int64_t)item * a_stride;
+    if (a64 >= a_end) break;
+    const uint32_t a = (uint32_t)a64;
+    const int64_t o0 = occ_ptr[a], m = occ_ptr[a + 1] - o0;
+    if (m == 0) continue;
+    const uint32_t* occ_a = occ + o0;
+    const int dlim = source_scope(unit_ptr, unit_last, occ_a, m, dmin, max_d, min_cov, incr_total);
+    if (dlim < dmin) continue;
+    SketchArgs A{unit_ptr, ids, codes, unit_last, occ_a, m, n_kmers, a, min_cov - 1u, cand, max_cand, counters};
+    sketch_source(tbase, A, dmin, dlim, splits);
   }
   if (lane == 0) {
     if (incr_total) atomicAdd((unsigned long long*)(counters + 2), (unsigned long long)incr_total);
@@ -1464,6 +1783,44 @@ int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint
       unit_ptr, ids, unit_last, occ_ptr, occ, usplit, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov,
       (uint4*)cand, max_cand, counters);
   CFK_CHECK_LAUNCH("pair_candidates_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_sketch_bits(void) { return SK_BITS; }
+int cfk_sketch_warps_per_block(void) { return SK_WARPS; }
+
+int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, cfk_stream_t stream) {
+  if (n_units < 0) return fail(CFK_ERR_INVALID, "cfk_sketch_codes: n_units < 0");
+  if (n_units == 0) return CFK_OK;
+  sketch_codes_kernel<<<(unsigned)blocks_for(n_units, 8), 256, 0, (cudaStream_t)stream>>>(unit_ptr, ids, n_units, codes);
+  CFK_CHECK_LAUNCH("sketch_codes_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* unit_last,
+                    const int64_t* occ_ptr, const uint32_t* occ, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
+                    int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint32_t* cand,
+                    int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream) {
+  if (n_entries < 0 || n_entries >= (1ll << 32))
+    return fail(CFK_ERR_INVALID, "cfk_pair_sketch: need 0 <= n_entries < 2^32 (32-bit positions in the id array)");
+  if (n_kmers < 0 || n_kmers >= (1ll << 32) - 1) return fail(CFK_ERR_INVALID, "cfk_pair_sketch: bad n_kmers");
+  if (min_d < 0) return fail(CFK_ERR_INVALID, "cfk_pair_sketch: min_d < 0 is not defined by the reference loop");
+  if (min_cov < CFK_SKETCH_MIN_COV || min_cov > CFK_SKETCH_MAX_COV)
+    return fail(CFK_ERR_INVALID, "cfk_pair_sketch: min_cov outside [CFK_SKETCH_MIN_COV, CFK_SKETCH_MAX_COV]; use cfk_pair_candidates");
+  if (a_begin < 0 || a_end > n_kmers || a_stride < 1) return fail(CFK_ERR_INVALID, "cfk_pair_sketch: bad id range");
+  if (max_cand < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_pair_sketch: bad sizes");
+  if (a_begin >= a_end || max_d < (min_d > 1 ? min_d : 1)) return CFK_OK;
+  static bool attr_done = false;
+  const int smem = SK_WARPS * SK_WARP_BYTES;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(pair_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_pair_sketch: cudaFuncSetAttribute", e);
+    attr_done = true;
+  }
+  pair_sketch_kernel<<<(unsigned)n_blocks, SK_WARPS * 32, smem, (cudaStream_t)stream>>>(
+      unit_ptr, ids, codes, unit_last, occ_ptr, occ, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
+      max_cand, counters);
+  CFK_CHECK_LAUNCH("pair_sketch_kernel", 1);
   return CFK_OK;
 }
 

@@ -12,6 +12,7 @@ There is no CPU fallback: constructing an Engine without CUDA or without libcfk.
 """
 import contextlib
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -21,6 +22,7 @@ from ._lib import CfkError
 from .encode import check_k
 
 U32_MAX = 0xFFFFFFFF
+SKETCH_MIN_COV, SKETCH_MAX_COV = 3, 255  # include/cfk.h CFK_SKETCH_MIN_COV / CFK_SKETCH_MAX_COV
 
 
 def band_to_int(left, right):
@@ -97,6 +99,8 @@ class Engine:
         self.cand_hint = 1 << 20
         self.edge_hint = 1 << 20
         self.table_load = 0.6  # distinct k-mers <= occurrences, so the stage-A table is at most this full
+        # stage C kernel: "auto" = sketch where it applies, "exact" = always the exact tables, "sketch" = insist
+        self.pair_mode = os.environ.get("CFK_PAIR_MODE", "auto")
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
 
     # ---- plumbing ---------------------------------------------------------------------------
@@ -340,18 +344,34 @@ class Engine:
             return empty
         occ_ptr, occ = occurrences if occurrences is not None else self.build_occurrences(csr, n_kmers, unit_lo, unit_hi)
         min_cov_u = int(min(max(min_cov, 0), U32_MAX))
-        usplit = self._empty(7 * csr.n_units, t.int32)
-        _lib.call("cfk_unit_splits", self._p(csr.unit_ptr), self._p(csr.ids), csr.n_units, csr.n_entries, n_kmers,
-                  self._p(usplit), self._stream())
+        # stage C flavour: the sketch kernel serves min_cov in [3, 255]; the exact tables serve anything
+        use_sketch = self.pair_mode != "exact" and SKETCH_MIN_COV <= min_cov_u <= SKETCH_MAX_COV
+        if self.pair_mode == "sketch" and not use_sketch:
+            raise CfkError(f"pair_mode=sketch needs {SKETCH_MIN_COV} <= min_coverage <= {SKETCH_MAX_COV}")
+        if use_sketch:
+            codes = self._empty(csr.n_entries, t.int16)
+            with self._stage("sketch_codes"):
+                _lib.call("cfk_sketch_codes", self._p(csr.unit_ptr), self._p(csr.ids), csr.n_units, self._p(codes),
+                          self._stream())
+        else:
+            usplit = self._empty(7 * csr.n_units, t.int32)
+            _lib.call("cfk_unit_splits", self._p(csr.unit_ptr), self._p(csr.ids), csr.n_units, csr.n_entries, n_kmers,
+                      self._p(usplit), self._stream())
         max_cand = int(self.cand_hint)
         while True:
             cand = self._empty(max_cand * 4, t.int32)
             counters = self._counters()
             with self._stage("pair_candidates"):
-                _lib.call("cfk_pair_candidates", self._p(csr.unit_ptr), self._p(csr.ids), self._p(unit_last),
-                          self._p(occ_ptr), self._p(occ), self._p(usplit), csr.n_entries, n_kmers, a_begin, a_end,
-                          a_stride, int(min_d), int(max_d), min_cov_u, self._p(cand), max_cand, self._p(counters),
-                          self.n_sms, self._stream())
+                if use_sketch:
+                    _lib.call("cfk_pair_sketch", self._p(csr.unit_ptr), self._p(csr.ids), self._p(codes),
+                              self._p(unit_last), self._p(occ_ptr), self._p(occ), csr.n_entries, n_kmers, a_begin, a_end,
+                              a_stride, int(min_d), int(max_d), min_cov_u, self._p(cand), max_cand, self._p(counters),
+                              self.n_sms, self._stream())
+                else:
+                    _lib.call("cfk_pair_candidates", self._p(csr.unit_ptr), self._p(csr.ids), self._p(unit_last),
+                              self._p(occ_ptr), self._p(occ), self._p(usplit), csr.n_entries, n_kmers, a_begin, a_end,
+                              a_stride, int(min_d), int(max_d), min_cov_u, self._p(cand), max_cand, self._p(counters),
+                              self.n_sms, self._stream())
             c = counters.cpu()
             self.last_pair_counters = [int(x) for x in c.tolist()]
             n_cand = int(c[0])

@@ -43,6 +43,15 @@ extern "C" {
 #define CFK_PAIR_TABLE_BYTES 11264 /* shared-memory counting table of one warp (multiple of 16) */
 #endif
 
+#ifndef CFK_SKETCH_BITS
+#define CFK_SKETCH_BITS 13        /* log2 of the byte counters in one warp's stage-C sketch (10..15) */
+#endif
+#ifndef CFK_SKETCH_LOAD_DIV
+#define CFK_SKETCH_LOAD_DIV 4     /* a sketch pass is planned for <= 2^CFK_SKETCH_BITS / this many cloud entries */
+#endif
+#define CFK_SKETCH_MIN_COV 3      /* cfk_pair_sketch serves min_cov in [3, 255]; cfk_pair_candidates serves any */
+#define CFK_SKETCH_MAX_COV 255
+
 typedef void* cfk_stream_t;
 
 int cfk_abi_version(void);
@@ -174,6 +183,23 @@ int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint
                         int64_t n_kmers, int64_t a_begin, int64_t a_end, int32_t a_stride,
                         int32_t min_d, int32_t max_d, uint32_t min_cov,
                         uint32_t* cand, int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
+
+/* The same contract as cfk_pair_candidates (same reference lines, same counters, same
+ * (a, b, d0, d1) output consumed by cfk_pair_join) for CFK_SKETCH_MIN_COV <= min_cov <=
+ * CFK_SKETCH_MAX_COV, an order of magnitude cheaper: instead of exact per-(a, b) counters a warp
+ * keeps 2^CFK_SKETCH_BITS saturating byte counters indexed by a hash of b -- an upper bound of
+ * sum_d cnt[d][a][b] -- and only ids whose counter reaches min_cov enter a small exact set that
+ * is emitted.  The emitted pairs are a SUPERSET of the pairs whose chunk total reaches min_cov;
+ * cfk_pair_join computes the exact counts either way, so the edges are identical.
+ * codes = cfk_sketch_codes output: per cloud entry the hash of its id (low CFK_SKETCH_BITS
+ * bits) and, in bit 15, whether another id of the same unit with the same hash precedes it. */
+int cfk_sketch_bits(void);
+int cfk_sketch_warps_per_block(void);
+int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, cfk_stream_t stream);
+int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* unit_last,
+                    const int64_t* occ_ptr, const uint32_t* occ, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
+                    int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov,
+                    uint32_t* cand, int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
 
 /* Replaces both loops of filter_dist_tuples, distance_based_kmer_recruitment.py:131-149, for
  * the pair candidates: joins the occurrence lists of a and b to get the exact cnt[d][a][b] for

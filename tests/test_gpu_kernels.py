@@ -33,6 +33,14 @@ def test_exclusive_scan(eng, n):
     assert np.array_equal(out[: n + 1], want)
 
 
+@pytest.fixture(params=["exact", "sketch"])
+def pair_mode(eng, request):
+    """Both stage-C kernels: exact shared-memory tables and the counter sketch (3 <= min_cov <= 255)."""
+    old, eng.pair_mode = eng.pair_mode, request.param
+    yield request.param
+    eng.pair_mode = old
+
+
 def _csr_from_units(units, n_kmers):
     """units: list (per read) of lists (per unit) of sorted id arrays."""
     flat = [u for rd in units for u in rd]
@@ -77,7 +85,7 @@ def _run_dist(eng, units, n_kmers, min_d, max_d, min_cov, **kw):
     return {tuple(int(x) for x in row) for row in e}, sel, res
 
 
-def test_dist_table_splitting(eng):
+def test_dist_table_splitting(eng, pair_mode):
     """Clouds far larger than one warp table force the id-range splitting path."""
     rng = np.random.default_rng(1)
     n_kmers = 6000
@@ -90,7 +98,7 @@ def test_dist_table_splitting(eng):
     assert sel == {e[0] for e in want} | {e[1] for e in want}
 
 
-def test_dist_wide_slots_and_long_lists(eng):
+def test_dist_wide_slots_and_long_lists(eng, pair_mode):
     """An id present in > 32 units of one read (multi-chunk occurrence list) in a universe too large for
     32-bit slots: exercises the 64-bit table and counts > 1 per read."""
     rng = np.random.default_rng(2)
@@ -105,6 +113,63 @@ def test_dist_wide_slots_and_long_lists(eng):
     dense_units = units
     want, incr = _numpy_edges(dense_units, n_real, 2, 40, 4)
     got, sel, res = _run_dist(eng, units, n_kmers, 2, 40, 4)
+    assert res.n_increments == incr
+    assert got == want
+
+
+_SAT_CACHE = {}
+
+
+def _saturation_case(min_cov):
+    if min_cov not in _SAT_CACHE:
+        rng = np.random.default_rng(7)
+        n_kmers = 1500
+        core = np.arange(0, 500, 2)            # 250 ids present in every unit of the long read: all hot together
+        rd = [np.sort(np.concatenate([core, rng.choice(np.arange(501, 1400), size=40, replace=False)]))
+              for _ in range(100)]
+        noise = [[np.sort(rng.choice(1400, size=rng.integers(1, 200), replace=False)) for _ in range(rng.integers(1, 6))]
+                 for _ in range(30)]
+        # P = 1450 then, five units later, Q = 1451 in 260 short reads and R = 1452 in 254 of them:
+        # cnt[5][P][Q] = 260 and cnt[5][P][R] = 254 sit on either side of min_cov = 255
+        pairs = [[np.array([1450, int(rng.integers(0, 1400))]), *[np.empty(0, np.int64)] * 4,
+                  np.array([1451, 1452] if i < 254 else [1451])] for i in range(260)]
+        units = [rd] + noise + pairs
+        _SAT_CACHE[min_cov] = (units, n_kmers) + _numpy_edges(units, n_kmers, 1, 12, min_cov)
+    return _SAT_CACHE[min_cov]
+
+
+@pytest.mark.parametrize("min_cov", [3, 254, 255])
+def test_dist_sketch_saturation_and_set_overflow(eng, pair_mode, min_cov):
+    """Counts far above the 8-bit sketch counters (a pair co-occurring in > 255 unit pairs), min_cov at both ends of
+    the sketch range, and more simultaneous hot ids than the level-2 set holds (forces the id-range split)."""
+    units, n_kmers, want, incr = _saturation_case(min_cov)
+    got, sel, res = _run_dist(eng, units, n_kmers, 1, 12, min_cov)
+    assert res.n_increments == incr
+    assert got == want
+    assert sel == {e[0] for e in want} | {e[1] for e in want}
+    assert (1450, 1451, 5, 260) in got and ((1450, 1452, 5, 254) in got) == (min_cov <= 254)
+    if pair_mode == "sketch":
+        assert res.n_splits > 0
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_dist_sketch_random_clouds(eng, pair_mode, seed):
+    """Random ragged clouds (empty units, one-unit reads, ids shared between neighbouring units)."""
+    rng = np.random.default_rng(100 + seed)
+    n_kmers = int(rng.integers(50, 700))
+    units = []
+    for _ in range(int(rng.integers(1, 60))):
+        n_u = int(rng.integers(1, 40))
+        base = rng.choice(n_kmers, size=min(n_kmers, int(rng.integers(1, 90))), replace=False)
+        rd = []
+        for _ in range(n_u):
+            keep = base[rng.random(base.size) < 0.7]
+            extra = rng.choice(n_kmers, size=int(rng.integers(0, 30)), replace=False)
+            rd.append(np.unique(np.concatenate([keep, extra])) if rng.random() > 0.1 else np.empty(0, np.int64))
+        units.append(rd)
+    min_cov = int(rng.integers(3, 7))
+    want, incr = _numpy_edges(units, n_kmers, 1, 150, min_cov)
+    got, sel, res = _run_dist(eng, units, n_kmers, 1, 150, min_cov)
     assert res.n_increments == incr
     assert got == want
 

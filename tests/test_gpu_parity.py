@@ -28,8 +28,18 @@ def _csr_of(clouds, k):
     return np.diff(st.read_unit_ptr), unit_ptr, keys[ids]
 
 
+@pytest.fixture(params=["auto", "exact"])
+def pair_mode(request):
+    """Stage C flavour: auto = sketch kernel where min_coverage allows it, exact = always the exact tables."""
+    from centroflye_b200.engine import default_engine
+    eng = default_engine()
+    old, eng.pair_mode = eng.pair_mode, request.param
+    yield request.param
+    eng.pair_mode = old
+
+
 @pytest.mark.parametrize("case,pi", all_case_points())
-def test_recruitment_matches_reference(golden, mods, case, pi, tmp_path):
+def test_recruitment_matches_reference(golden, mods, case, pi, tmp_path, pair_mode):
     dbkr, rkc, NCRF_Report = mods
     g = golden(case)
     meta, arr = g.point(pi)

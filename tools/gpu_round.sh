@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
 echo "== pytest gpu =="
-timeout -k 10 1200 python -m pytest tests -m gpu -x -q 2>&1 > gpurun_out/pytest_gpu.log; tail -6 gpurun_out/pytest_gpu.log
+timeout -k 10 1200 python -m pytest tests -m gpu -x -q --durations=12 2>&1 > gpurun_out/pytest_gpu.log; tail -6 gpurun_out/pytest_gpu.log
 echo "== smoke =="
 timeout -k 10 300 python __graft_entry__.py --smoke 2>&1 | tail -3 | tee gpurun_out/smoke.log
 echo "== bench full =="
@@ -18,7 +18,7 @@ timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 tail -2 gpurun_out/ncu_launches.log
 echo "== ncu full =="
-timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:'pair_candidates_kernel|docfreq_kernel|cloud_build_kernel|pair_join_kernel' -s 12 -c 4 \
+timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:'pair_sketch_kernel|docfreq_kernel|cloud_build_kernel|pair_join_kernel' -s 12 -c 4 \
    -f -o gpurun_out/prof_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 ls -la gpurun_out
