@@ -147,9 +147,9 @@ def run_ours(args):
         reads = eng.upload_reads(batch, k)
         dunits = eng.upload_units(units, k)
         index, csr, res = device_step(reads, dunits)
-        out = (res.selected.cpu(), res.edges.cpu(), csr.unit_ptr.cpu(), csr.ids.cpu(), index.sorted_keys.cpu())
-        torch.cuda.synchronize()
-        d2h = sum(t.numel() * t.element_size() for t in out)
+        out = eng.to_host(selected=res.selected, edges=res.edges, unit_ptr=csr.unit_ptr, ids=csr.ids,
+                          rare_keys=index.sorted_keys)  # pinned result buffers; synchronises
+        d2h = sum(t.numel() * t.element_size() for t in out.values())
         return reads.h2d_bytes + dunits.h2d_bytes, d2h
 
     reads = eng.upload_reads(batch, k) if runner is None else None
@@ -227,7 +227,7 @@ def run_ours(args):
                    "unique_kmers": int(last.selected.numel()), "l2": "256 MiB flush write between timed steps",
                    "sharding": ("reads sharded by record; all-to-all of (k-mer, n_reads, n_multi) records, all-gather of rare "
                                 "keys and cloud CSR, sources dealt round-robin" if world > 1 else "single GPU")},
-        "roofline": {"kernel": "pair_candidates_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": getattr(eng, "last_pair_kernel", "pair_candidates_kernel"), "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
                      "peak_source": peak_src, "kernel_ms": dc_ms,
                      "algorithmic_bytes": alg_bytes, "note": "32 B per pair increment (BASELINE.md §4); counting "

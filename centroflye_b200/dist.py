@@ -177,9 +177,9 @@ class ShardedRecruiter:
         self.reads = eng.upload_reads(self.batch, self.k)
         self.dunits = eng.upload_units(self.units, self.k)
         index, csr, res = self.step(lo, hi, max_nonuniq, min_d, max_d, min_cov)
-        out = [csr.unit_ptr.cpu(), csr.ids.cpu()]
+        want = dict(unit_ptr=csr.unit_ptr, ids=csr.ids)
         if self.rank == 0:
-            out += [res.selected.cpu(), res.edges.cpu(), index.sorted_keys.cpu()]
-        self.torch.cuda.synchronize()
-        d2h = sum(x.numel() * x.element_size() for x in out)
+            want.update(selected=res.selected, edges=res.edges, rare_keys=index.sorted_keys)
+        out = eng.to_host(**want)  # pinned result buffers; synchronises
+        d2h = sum(x.numel() * x.element_size() for x in out.values())
         return self.reads.h2d_bytes + self.dunits.h2d_bytes, d2h

@@ -102,6 +102,7 @@ class Engine:
         # stage C kernel: "auto" = sketch where it applies, "exact" = always the exact tables, "sketch" = insist
         self.pair_mode = os.environ.get("CFK_PAIR_MODE", "auto")
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
+        self._host_pool = {}  # name -> pinned uint8 buffer for results (to_host)
 
     # ---- plumbing ---------------------------------------------------------------------------
     def _stream(self):
@@ -112,6 +113,37 @@ class Engine:
         if dtype is not None:
             t = t.to(dtype)
         return t.pin_memory().to(self.device, non_blocking=True)
+
+    def _staged(self, owner, name, arr):
+        """Pinned staging copy of a host array, made once per owner object (ReadBatch / UnitIndex are immutable
+        after ingestion) and reused by every later upload: page-locking 40 MB costs more than copying it."""
+        cache = owner.__dict__.setdefault("_cfk_pinned", {})
+        hit = cache.get(name)
+        if hit is None or hit[0] is not arr:
+            src = np.ascontiguousarray(arr)
+            src = src.view(np.int32) if src.dtype == np.uint32 else src
+            hit = (arr, self.torch.from_numpy(src).pin_memory())
+            cache[name] = hit
+        return hit[1].to(self.device, non_blocking=True)
+
+    def to_host(self, **tensors):
+        """Device tensors -> host tensors through pinned result buffers kept by the engine (one stream-ordered
+        copy each, one synchronize at the end).  The returned tensors alias the pool: they are valid until the
+        next to_host() call with the same names."""
+        t = self.torch
+        out = {}
+        for name, src in tensors.items():
+            src = src.contiguous()
+            nbytes = src.numel() * src.element_size()
+            buf = self._host_pool.get(name)
+            if buf is None or buf.numel() < nbytes:
+                buf = t.empty(max(nbytes + nbytes // 8, 1 << 16), dtype=t.uint8, pin_memory=True)
+                self._host_pool[name] = buf
+            dst = buf[:nbytes].view(src.dtype).view(src.shape)
+            dst.copy_(src, non_blocking=True)
+            out[name] = dst
+        t.cuda.current_stream(self.device).synchronize()
+        return out
 
     def _empty(self, n, dtype):
         return self.torch.empty(max(int(n), 1), dtype=dtype, device=self.device)
@@ -156,8 +188,9 @@ class Engine:
         order = np.argsort(-batch.read_len, kind="stable").astype(np.int32)
         packed = batch.packed.view(np.int32)
         h2d = packed.nbytes + batch.read_off.nbytes + batch.read_len.nbytes + order.nbytes
-        return DeviceReads(packed=self._to_dev(packed), read_off=self._to_dev(batch.read_off),
-                           read_len=self._to_dev(batch.read_len), order=self._to_dev(order),
+        return DeviceReads(packed=self._staged(batch, "packed", batch.packed),
+                           read_off=self._staged(batch, "read_off", batch.read_off),
+                           read_len=self._staged(batch, "read_len", batch.read_len), order=self._to_dev(order),
                            n_reads=batch.n_reads, n_bases=batch.n_bases, h2d_bytes=h2d)
 
     def upload_units(self, units, k):
@@ -169,7 +202,8 @@ class Engine:
         counts = np.diff(ptr)
         last[:] = np.repeat(ptr[1:] - 1, counts)
         h2d = units.unit_off.nbytes + units.unit_len.nbytes + kbase.nbytes + last.nbytes
-        return DeviceUnits(unit_off=self._to_dev(units.unit_off), unit_len=self._to_dev(units.unit_len),
+        return DeviceUnits(unit_off=self._staged(units, "unit_off", units.unit_off),
+                           unit_len=self._staged(units, "unit_len", units.unit_len),
                            unit_kbase=self._to_dev(kbase), unit_last=self._to_dev(last), n_units=units.n_units,
                            n_kmer_starts=int(kbase[-1]), h2d_bytes=h2d)
 
@@ -374,6 +408,7 @@ class Engine:
                               self.n_sms, self._stream())
             c = counters.cpu()
             self.last_pair_counters = [int(x) for x in c.tolist()]
+            self.last_pair_kernel = "pair_sketch_kernel" if use_sketch else "pair_candidates_kernel"
             n_cand = int(c[0])
             if n_cand <= max_cand:
                 break

@@ -148,7 +148,7 @@ def test_dist_sketch_saturation_and_set_overflow(eng, pair_mode, min_cov):
     assert got == want
     assert sel == {e[0] for e in want} | {e[1] for e in want}
     assert (1450, 1451, 5, 260) in got and ((1450, 1452, 5, 254) in got) == (min_cov <= 254)
-    if pair_mode == "sketch":
+    if pair_mode == "sketch" and min_cov == 3:  # only at a low threshold do all 250 core ids turn hot in one pass
         assert res.n_splits > 0
 
 
