@@ -147,11 +147,13 @@ class ShardedRecruiter:
         from .engine import DistResult
         eng, t = self.eng, self.torch
         table = eng.count_docfreq(self.reads, self.k)
-        rare = self.global_rare_keys(table, lo, hi, max_nonuniq)
+        with eng._stage("exchange_docfreq"):
+            rare = self.global_rare_keys(table, lo, hi, max_nonuniq)
         del table
         index = eng.build_index(rare, presorted=True)
         csr = eng.build_clouds(self.reads, self.dunits, self.k, index)
-        gcsr, unit_last = self.global_clouds(csr)
+        with eng._stage("gather_clouds"):
+            gcsr, unit_last = self.global_clouds(csr)
         res = eng.dist_edges(gcsr, unit_last, index.n, min_d, max_d, min_cov, rel_threshold,
                              a_begin=self.rank, a_stride=self.world)
         stats = t.tensor([res.n_increments, res.n_candidates, res.n_pair_candidates, res.n_splits], dtype=t.int64,
@@ -160,12 +162,13 @@ class ShardedRecruiter:
         self.last_increments = int(stats[0].item())
         if not gather:
             return index, csr, res
-        edges, _ = all_gather_v(res.edges.reshape(-1).contiguous(), self.group)
-        flags = eng._zeros(index.n, t.int32)
-        if res.selected.numel():
-            flags[res.selected.to(t.int64)] = 1
-        self.dist.all_reduce(flags, op=self.dist.ReduceOp.MAX, group=self.group)
-        selected = t.nonzero(flags[: index.n]).reshape(-1).to(t.int32)
+        with eng._stage("gather_edges"):
+            edges, _ = all_gather_v(res.edges.reshape(-1).contiguous(), self.group)
+            flags = eng._zeros(index.n, t.int32)
+            if res.selected.numel():
+                flags[res.selected.to(t.int64)] = 1
+            self.dist.all_reduce(flags, op=self.dist.ReduceOp.MAX, group=self.group)
+            selected = t.nonzero(flags[: index.n]).reshape(-1).to(t.int32)
         s = stats.cpu().tolist()
         out = DistResult(edges=edges.view(-1, 4), selected=selected, n_candidates=s[1], n_increments=s[0],
                          n_splits=s[3], n_pair_candidates=s[2])

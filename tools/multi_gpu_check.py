@@ -33,7 +33,11 @@ def main():
     kw = dict(median_len=7000, sigma=0.4, min_len=5200, max_len=20000)
     reads = synth.simulate_reads(genome, a0, alen, unit, 20, 0.05, 7, **kw)
     mine = synth.simulate_reads(genome, a0, alen, unit, 20, 0.05, 7, shard=(rank, world), **kw)
-    assert [r.r_id for r in mine] == [r.r_id for r in reads[rank::world]]
+    all_ids = {r.r_id for r in reads}
+    assert all(r.r_id in all_ids for r in mine), "shard holds a read that is not in the whole set"
+    n_mine = torch.tensor([len(mine)], dtype=torch.int64, device=f"cuda:{local}")
+    dist.all_reduce(n_mine)
+    assert int(n_mine.item()) == len(reads), "shards do not partition the read set"
     k, max_nonuniq, min_d, max_d, min_cov = 19, 3, 1, 150, 4
     lo, hi = band_to_int(0.9 * 20 * 0.4, 3.0 * 20 * 0.4)
     batch, units = batch_from_synth(mine, len(unit))
