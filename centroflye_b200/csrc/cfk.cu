@@ -103,9 +103,9 @@ constexpr int DF_SET_SLOTS = CFK_DOCFREQ_SET_SLOTS;   // u32 slots of the per-re
 constexpr int DF_SET_FILL = DF_SET_SLOTS * 53 / 100;  // k-mers planned per pass
 constexpr uint32_t DF_MULTI = 0x80000000u;
 
-// find-or-insert in the global table; returns the slot or -1 if full
-__device__ __forceinline__ int64_t slot_upsert(uint64_t* table, int64_t cap, uint64_t key, uint64_t h) {
-  int64_t slot = home_slot(h, cap);
+// find-or-insert in the global table, probing linearly from `slot` (may equal cap: wraps); returns the slot or -1 if full
+__device__ __forceinline__ int64_t slot_upsert(uint64_t* table, int64_t cap, uint64_t key, int64_t slot) {
+  if (slot >= cap) slot = 0;
   for (int64_t probes = 0; probes < cap; ++probes) {
     const uint64_t cur = ((volatile uint64_t*)table)[2 * slot];
     if (cur == key) return slot;
@@ -169,37 +169,67 @@ docfreq_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ 
           const int p = p0 + i;
           kmer = (kmer << 2) | ((s_words[p >> 4] >> ((p & 15) << 1)) & 3u);
         }
-        const int pend = min(p0 + DF_PER_THREAD, npos);
-        for (int p = p0; p < pend; ++p) {
+        // phase 1: the read's own set (shared memory).  act holds 2 bits per k-mer of this thread:
+        // 1 = first sighting in this read (n_reads += 1), 2 = second sighting (n_multi += 1).
+        uint64_t km[DF_PER_THREAD];
+        uint32_t act = 0;
+#pragma unroll
+        for (int j = 0; j < DF_PER_THREAD; ++j) {
+          const int p = p0 + j;
+          km[j] = 0;
+          if (p >= npos) continue;
           const int q = p + k - 1;
           kmer = ((kmer << 2) | ((s_words[q >> 4] >> ((q & 15) << 1)) & 3u)) & mask;
+          km[j] = kmer;
           if (n_pass > 1 && __umulhi((uint32_t)(kmer ^ (kmer >> 32)) * 0x9E3779B1u, n_pass) != pass) continue;
-          const uint64_t h = mix64(kmer);
           const uint32_t pos = (uint32_t)(tile0 + p);
-          uint32_t s = __umulhi((uint32_t)h, c_eff);
+          uint32_t s = __umulhi((uint32_t)mix64(kmer), c_eff);
           uint32_t probes = 0;
           for (; probes < c_eff; ++probes) {
             uint32_t v = ((volatile uint32_t*)set)[s];
             if (v == 0) {
               v = atomicCAS(set + s, 0u, pos + 1);
               if (v == 0) {  // first sighting of this k-mer in this read
-                const int64_t slot = slot_upsert(table, cap, kmer, h);
-                if (slot < 0) counters[0] = 1;
-                else atomicAdd(reinterpret_cast<uint32_t*>(table + 2 * slot + 1), 1u);
+                act |= 1u << (2 * j);
                 break;
               }
             }
             if (kmer_at(words, (v & ~DF_MULTI) - 1, k) == kmer) {
-              if (!(v & DF_MULTI) && !(atomicOr(set + s, DF_MULTI) & DF_MULTI)) {  // exactly one thread flips the bit
-                const int64_t slot = slot_upsert(table, cap, kmer, h);
-                if (slot < 0) counters[0] = 1;
-                else atomicAdd(reinterpret_cast<uint32_t*>(table + 2 * slot + 1) + 1, 1u);
-              }
+              if (!(v & DF_MULTI) && !(atomicOr(set + s, DF_MULTI) & DF_MULTI)) act |= 2u << (2 * j);  // exactly one thread flips the bit
               break;
             }
             if (++s == c_eff) s = 0;
           }
           if (probes == c_eff) counters[1] = 1;  // cannot happen: a pass is planned for <= 53 % load
+        }
+        if (act == 0) continue;
+        // phase 2: the global table, four independent claims in flight per thread (the table is far larger than L2:
+        // every probe is a DRAM round trip, so the round trips must overlap).  The claim itself is the probe:
+        // CAS(EMPTY -> key) returns EMPTY (claimed) or the resident key.
+#pragma unroll
+        for (int half = 0; half < DF_PER_THREAD / 4; ++half) {
+          if (((act >> (8 * half)) & 0xFFu) == 0) continue;
+          int64_t slot[4];
+          uint64_t old[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int jj = half * 4 + j;
+            slot[j] = home_slot(mix64(km[jj]), cap);
+            old[j] = km[jj];
+            if ((act >> (2 * jj)) & 3u)
+              old[j] = atomicCAS((unsigned long long*)(table + 2 * slot[j]), (unsigned long long)EMPTY,
+                                 (unsigned long long)km[jj]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int jj = half * 4 + j;
+            const uint32_t what = (act >> (2 * jj)) & 3u;
+            if (!what) continue;
+            int64_t sl = slot[j];
+            if (old[j] != EMPTY && old[j] != km[jj]) sl = slot_upsert(table, cap, km[jj], sl + 1);
+            if (sl < 0) counters[0] = 1;
+            else atomicAdd(reinterpret_cast<uint32_t*>(table + 2 * sl + 1) + (what >> 1), 1u);
+          }
         }
       }
     }
@@ -217,7 +247,7 @@ __global__ void table_merge_kernel(const uint64_t* __restrict__ keys, const uint
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t key = keys[i];
-  int64_t slot = slot_upsert(table, cap, key, mix64(key));
+  int64_t slot = slot_upsert(table, cap, key, home_slot(mix64(key), cap));
   if (slot < 0) { counters[0] = 1; return; }
   uint32_t* cnt = reinterpret_cast<uint32_t*>(table + 2 * slot + 1);
   if (nreads[i]) atomicAdd(cnt, nreads[i]);
@@ -1191,20 +1221,28 @@ pair_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __r
 // ============================================================================================
 constexpr int SK_BITS = CFK_SKETCH_BITS;
 constexpr int SK_TBL_BYTES = 1 << SK_BITS;
-constexpr uint32_t SK_OFF_MASK = (uint32_t)SK_TBL_BYTES - 1u;
-constexpr uint32_t SK_DUP = 0x8000u;
-constexpr uint32_t SK_INV = 0xFFFFFFFFu;
+constexpr uint32_t SK_OFF_MASK = 0x3FFFu;          // code bits 0..13: byte offset in the warp's table (hash, or the null byte)
+constexpr uint32_t SK_DUP = 0x8000u;               // code bit 15: do not store (duplicate hash inside the unit, or null)
+constexpr uint32_t SK_NULL = SK_DUP | (uint32_t)SK_TBL_BYTES;  // padding entry: reads the always-zero byte behind the table
+constexpr int SK_PAD_BYTES = 16;                   // that byte (and alignment of what follows)
 constexpr int SK_L2_SLOTS = 256;   // level-2 set, u32 slots holding b + 1
 constexpr int SK_L2_MAX = 192;
 constexpr int SK_Q_SLOTS = 256;    // queue of hot positions
-constexpr int SK_WINDOW = 128;     // cloud entries per step (4 per lane)
-constexpr int SK_WARP_BYTES = SK_TBL_BYTES + SK_L2_SLOTS * 4 + SK_Q_SLOTS * 4;
+constexpr int SK_WINDOW = 128;     // cloud entries per step (4 per lane) = one block of codes[]
+constexpr int SK_WARP_BYTES = SK_TBL_BYTES + SK_PAD_BYTES + SK_L2_SLOTS * 4 + SK_Q_SLOTS * 4;
 constexpr int SK_WARPS_FIT = (227 * 1024 - 256) / SK_WARP_BYTES;
 constexpr int SK_WARPS = SK_WARPS_FIT > 32 ? 32 : SK_WARPS_FIT;
 constexpr uint32_t SK_CAP = (uint32_t)SK_TBL_BYTES / CFK_SKETCH_LOAD_DIV;  // planned cloud entries per pass
 constexpr int SK_ND_MAX = 16;
-static_assert(SK_BITS >= 10 && SK_BITS <= 15, "codes are 16 bit: hash in the low bits, bit 15 = duplicate flag");
+static_assert(SK_BITS >= 10 && SK_BITS <= 13, "codes are 16 bit: offset in bits 0..13 (the null byte sits at 2^SK_BITS), bit 15 = no store");
 static_assert(SK_WARPS >= 1, "sketch does not fit shared memory");
+
+// codes[] layout (private to the two sketch kernels): blocks of SK_WINDOW codes; unit u owns the blocks
+// sk_block(unit_ptr[u], u) .. + ceil(|C_u| / SK_WINDOW) - 1 (closed form, no scan: consecutive units are at least
+// that far apart).  Inside a block the entry 32 * j + l of the window sits at 4 * l + j, so lane l fetches its four
+// entries -- one per row j -- with ONE 8-byte load; slots behind the end of the unit hold SK_NULL.
+__host__ __device__ __forceinline__ int64_t sk_block(int64_t first_entry, int64_t unit) { return (first_entry >> 7) + unit; }
+static_assert(SK_WINDOW == 128, "sk_block shifts by 7");
 
 __device__ __forceinline__ uint32_t sk_hash(uint32_t id) { return (id * 0x9E3779B1u) >> (32 - SK_BITS); }
 
@@ -1220,9 +1258,10 @@ __device__ __forceinline__ uint32_t atom_cas_shared(uint32_t a, uint32_t cmp, ui
   return old;
 }
 
-// codes[p] = hash of ids[p] | SK_DUP if an earlier-served id of the same unit has the same hash.  Warp per unit.
+// Per cloud entry: hash of the id | SK_DUP if another id of the same unit with the same hash was served first, written
+// in the blocked layout above.  Warp per unit.
 __global__ void __launch_bounds__(256) sketch_codes_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
-                                                           int64_t n_units, uint16_t* __restrict__ codes) {
+                                                           int64_t n_units, uint2* __restrict__ codes) {
   __shared__ uint32_t bm[8][SK_TBL_BYTES / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t u = (int64_t)blockIdx.x * 8 + warp;
@@ -1231,17 +1270,27 @@ __global__ void __launch_bounds__(256) sketch_codes_kernel(const int64_t* __rest
   if (b == e) return;
   for (int i = lane; i < SK_TBL_BYTES / 32; i += 32) bm[warp][i] = 0;
   __syncwarp();
-  for (int64_t p = b + lane; p < e; p += 32) {
-    const uint32_t h = sk_hash(ids[p]);
-    const uint32_t old = atomicOr(&bm[warp][h >> 5], 1u << (h & 31u));
-    codes[p] = (uint16_t)(h | (((old >> (h & 31u)) & 1u) ? SK_DUP : 0u));
+  uint2* out = codes + sk_block(b, u) * 32 + lane;
+  for (int64_t p0 = b; p0 < e; p0 += SK_WINDOW, out += 32) {
+    uint32_t c[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t p = p0 + 32 * j + lane;
+      c[j] = SK_NULL;
+      if (p < e) {
+        const uint32_t h = sk_hash(ids[p]);
+        const uint32_t old = atomicOr(&bm[warp][h >> 5], 1u << (h & 31u));
+        c[j] = h | (((old >> (h & 31u)) & 1u) ? SK_DUP : 0u);
+      }
+    }
+    *out = make_uint2(c[0] | (c[1] << 16), c[2] | (c[3] << 16));
   }
 }
 
 struct SketchArgs {
   const int64_t* __restrict__ unit_ptr;
   const uint32_t* __restrict__ ids;
-  const uint16_t* __restrict__ codes;
+  const uint2* __restrict__ codes;
   const uint32_t* __restrict__ unit_last;
   const uint32_t* __restrict__ occ_a;
   int64_t m;
@@ -1252,15 +1301,6 @@ struct SketchArgs {
   int64_t max_cand;
   int64_t* counters;
 };
-
-// the four codes of this lane in the window starting at position p of a unit list ending at e
-__device__ __forceinline__ void sk_load(const SketchArgs& A, uint32_t p, uint32_t e, int lane, uint32_t (&c)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t q = p + (uint32_t)lane + 32u * i;
-    c[i] = (q < e) ? (uint32_t)__ldg(A.codes + q) : SK_INV;
-  }
-}
 
 // queued hot positions -> level-2 set.  Returns false if the set overflowed.
 __device__ bool sk_drain(uint32_t l2base, uint32_t qbase, const SketchArgs& A, int qn, int64_t lo_id, int64_t hi_id,
@@ -1298,34 +1338,37 @@ __device__ bool sk_drain(uint32_t l2base, uint32_t qbase, const SketchArgs& A, i
 __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, int64_t lo_id, int64_t hi_id) {
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
-  const uint32_t l2base = tbase + SK_TBL_BYTES, qbase = l2base + SK_L2_SLOTS * 4;
+  const uint32_t l2base = tbase + SK_TBL_BYTES + SK_PAD_BYTES, qbase = l2base + SK_L2_SLOTS * 4;
+  const uint32_t thr = A.thr;
 #pragma unroll 4
-  for (int i = lane; i < (SK_TBL_BYTES + SK_L2_SLOTS * 4) / 16; i += 32) sts128(tbase + (uint32_t)i * 16u, make_uint4(0, 0, 0, 0));
+  for (int i = lane; i < (SK_TBL_BYTES + SK_PAD_BYTES + SK_L2_SLOTS * 4) / 16; i += 32)
+    sts128(tbase + (uint32_t)i * 16u, make_uint4(0, 0, 0, 0));
   __syncwarp();
   int qn = 0, claims = 0;
   const int64_t n_items = A.m * (int64_t)nd;
   for (int64_t i0 = 0; i0 < n_items; i0 += 32) {
     const int64_t it = i0 + lane;
-    uint32_t up = 0, ue = 0;  // this lane's unit list [up, ue)
+    uint32_t up = 0, ue = 0, ub = 0;  // this lane's unit: entries [up, ue) of ids[], first block of codes[]
     if (it < n_items) {
       const int64_t t = (nd == 1) ? it : it / nd;
       const int64_t g = (int64_t)__ldg(A.occ_a + t);
       const int64_t u = g + d0 + (it - t * nd);
       if (u <= (int64_t)__ldg(A.unit_last + g)) {
-        up = (uint32_t)__ldg(A.unit_ptr + u);
+        const int64_t p0 = __ldg(A.unit_ptr + u);
+        up = (uint32_t)p0;
         ue = (uint32_t)__ldg(A.unit_ptr + u + 1);
+        ub = (uint32_t)sk_block(p0, u);
       }
     }
     unsigned rest = __ballot_sync(FULL, ue > up);
     if (!rest) continue;
     int src = __ffs(rest) - 1;
     rest &= rest - 1;
-    uint32_t p = __shfl_sync(FULL, up, src), e = __shfl_sync(FULL, ue, src);
-    uint32_t c[4], n[4];
-    sk_load(A, p, e, lane, c);
+    uint32_t p = __shfl_sync(FULL, up, src), e = __shfl_sync(FULL, ue, src), cb = __shfl_sync(FULL, ub, src);
+    uint2 w = __ldg(A.codes + (size_t)cb * 32u + lane);
     for (;;) {
       // the next window (rest of this unit, else the next unit of the group): its codes fly during this step
-      uint32_t np = p + SK_WINDOW, ne = e;
+      uint32_t np = p + SK_WINDOW, ne = e, ncb = cb + 1u;
       bool more = true;
       if (np >= ne) {
         if (rest) {
@@ -1333,29 +1376,48 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
           rest &= rest - 1;
           np = __shfl_sync(FULL, up, src);
           ne = __shfl_sync(FULL, ue, src);
+          ncb = __shfl_sync(FULL, ub, src);
         } else {
           more = false;
         }
       }
-      if (more) sk_load(A, np, ne, lane, n);
-      // level 1: non-flagged entries of one unit have distinct hashes, so all stores of a step hit distinct bytes
-      uint32_t old[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) old[i] = (c[i] != SK_INV) ? lds_u8(tbase + (c[i] & SK_OFF_MASK)) : 0u;
-      uint32_t hot = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (c[i] != SK_INV) {
-          if (old[i] >= A.thr) hot |= 1u << i;
-          if (!(c[i] & SK_DUP)) sts_u8(tbase + (c[i] & SK_OFF_MASK), old[i] + (old[i] != 255u));
+      uint2 nw = make_uint2(0, 0);
+      if (more) nw = __ldg(A.codes + (size_t)ncb * 32u + lane);
+      // level 1, one row of 32 entries at a time (rows behind the end of the unit are skipped; padding inside the last
+      // row reads the null byte).  Non-flagged entries of one unit have distinct hashes, so all stores of a step hit
+      // distinct bytes: plain ld/st.
+      const uint32_t rem = e - p;
+      bool h0, h1 = false, h2 = false, h3 = false;
+      {
+        const uint32_t a0 = tbase + (w.x & SK_OFF_MASK);
+        const uint32_t o0 = lds_u8(a0);
+        if (!(w.x & SK_DUP)) sts_u8(a0, min(o0 + 1u, 255u));
+        h0 = o0 >= thr;
+      }
+      if (rem > 32u) {
+        const uint32_t a1 = tbase + ((w.x >> 16) & SK_OFF_MASK);
+        const uint32_t o1 = lds_u8(a1);
+        if ((int32_t)w.x >= 0) sts_u8(a1, min(o1 + 1u, 255u));
+        h1 = o1 >= thr;
+        if (rem > 64u) {
+          const uint32_t a2 = tbase + (w.y & SK_OFF_MASK);
+          const uint32_t o2 = lds_u8(a2);
+          if (!(w.y & SK_DUP)) sts_u8(a2, min(o2 + 1u, 255u));
+          h2 = o2 >= thr;
+          if (rem > 96u) {
+            const uint32_t a3 = tbase + ((w.y >> 16) & SK_OFF_MASK);
+            const uint32_t o3 = lds_u8(a3);
+            if ((int32_t)w.y >= 0) sts_u8(a3, min(o3 + 1u, 255u));
+            h3 = o3 >= thr;
+          }
         }
       }
-      if (__any_sync(FULL, hot != 0)) {
+      if (__any_sync(FULL, h0 | h1 | h2 | h3)) {
+        const bool hs[4] = {h0, h1, h2, h3};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const bool h = (hot >> i) & 1u;
-          const unsigned bal = __ballot_sync(FULL, h);
-          if (h) sts(qbase + (uint32_t)(qn + __popc(bal & lt)) * 4u, p + (uint32_t)lane + 32u * i);
+          const unsigned bal = __ballot_sync(FULL, hs[i]);
+          if (hs[i]) sts(qbase + (uint32_t)(qn + __popc(bal & lt)) * 4u, p + (uint32_t)lane + 32u * i);
           qn += __popc(bal);
         }
         if (qn > SK_Q_SLOTS - SK_WINDOW) {
@@ -1365,9 +1427,7 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
       }
       __syncwarp();
       if (!more) break;
-      p = np; e = ne;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) c[i] = n[i];
+      p = np; e = ne; cb = ncb; w = nw;
     }
   }
   if (!sk_drain(l2base, qbase, A, qn, lo_id, hi_id, claims)) return -1;
@@ -1429,13 +1489,15 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
     int64_t lo_id = 0, width = A.n_kmers;
     while (lo_id < A.n_kmers) {
       const int64_t hi_id = min(A.n_kmers, lo_id + width);
-      if (sketch_pass(tbase, A, d0, nd, lo_id, hi_id) < 0) {  // level-2 set overflow: fewer distances, then narrower id ranges
+      const int emitted = sketch_pass(tbase, A, d0, nd, lo_id, hi_id);
+      if (emitted < 0) {  // level-2 set overflow: fewer distances, then narrower id ranges
         ++splits;
         if (nd > 1) { nd_force = nd >> 1; redo = true; break; }
         width = max((int64_t)1, (hi_id - lo_id) >> 1);
         continue;
       }
       lo_id = hi_id;
+      if (emitted < SK_L2_MAX / 2 && width < A.n_kmers) width <<= 1;  // sparse stretch of the id space: widen again
     }
     if (redo) continue;
     d0 += nd;
@@ -1444,7 +1506,7 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
 }
 
 __global__ void __launch_bounds__(SK_WARPS * 32, 1)
-pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids, const uint16_t* __restrict__ codes,
+pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids, const uint2* __restrict__ codes,
                    const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
                    const uint32_t* __restrict__ occ, int64_t n_kmers, int64_t a_begin, int64_t a_end, int32_t a_stride,
                    int32_t min_d, int32_t max_d, uint32_t min_cov, uint4* cand, int64_t max_cand, int64_t* counters) {
@@ -1485,26 +1547,29 @@ __global__ void pair_join_kernel(const uint4* __restrict__ cand, int64_t n_cand,
                                  int32_t min_d, int32_t max_d, uint32_t min_cov, double rel_threshold, uint4* edges,
                                  int64_t max_edges, uint8_t* selected, int64_t* counters) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int dmin = max(min_d, 1);
+  const int64_t dmin = max(min_d, 1);
   uint4 c = make_uint4(0, 0, 0, 0);
   uint32_t dmask = 0;  // distances d0 + j of the chunk at which the pair co-occurs
+  uint32_t cnt0 = 0;   // cnt[d0][a][b], gathered by the first join (most chunks are a single distance)
   uint64_t all_occ = 0;
-  int64_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+  const uint32_t *oa = occ, *oa_end = occ, *ob = occ, *ob_end = occ;
   if (i < n_cand) {
     c = cand[i];
-    a0 = occ_ptr[c.x]; a1 = occ_ptr[c.x + 1];
-    b0 = occ_ptr[c.y]; b1 = occ_ptr[c.y + 1];
-    int64_t j = b0;
-    for (int64_t t = a0; t < a1; ++t) {
-      const int64_t g = __ldg(occ + t);
+    oa = occ + occ_ptr[c.x]; oa_end = occ + occ_ptr[c.x + 1];
+    ob = occ + occ_ptr[c.y]; ob_end = occ + occ_ptr[c.y + 1];
+    const uint32_t* j = ob;
+    for (const uint32_t* t = oa; t < oa_end; ++t) {
+      const int64_t g = __ldg(t);
       const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, (int64_t)__ldg(unit_last + g));
       if (lo > hi) continue;
-      while (j < b1 && (int64_t)__ldg(occ + j) < lo) ++j;
-      for (int64_t jj = j; jj < b1; ++jj) {
-        const int64_t d = (int64_t)__ldg(occ + jj) - g;
-        if (d > hi - g) break;
+      while (j < ob_end && (int64_t)__ldg(j) < lo) ++j;
+      for (const uint32_t* jj = j; jj < ob_end; ++jj) {
+        const int64_t u = __ldg(jj);
+        if (u > hi) break;
         ++all_occ;
-        if (d >= (int64_t)c.z && d <= (int64_t)c.w) dmask |= 1u << (int)(d - c.z);
+        const uint32_t dj = (uint32_t)(u - g) - c.z;  // wraps to a huge value below d0
+        if (dj <= c.w - c.z) dmask |= 1u << dj;
+        cnt0 += dj == 0u;
       }
     }
   }
@@ -1513,14 +1578,19 @@ __global__ void pair_join_kernel(const uint4* __restrict__ cand, int64_t n_cand,
     bool keep = false;
     uint32_t d = 0, cnt = 0;
     if (dmask) {
-      d = c.z + (uint32_t)(__ffs(dmask) - 1);
+      const uint32_t dj = (uint32_t)(__ffs(dmask) - 1);
+      d = c.z + dj;
       dmask &= dmask - 1;
-      int64_t j = b0;
-      for (int64_t t = a0; t < a1; ++t) {  // cnt[d][a][b]: occurrences g of a with g + d holding b inside the read
-        const int64_t g = __ldg(occ + t);
-        if (g + d > (int64_t)__ldg(unit_last + g)) continue;
-        while (j < b1 && (int64_t)__ldg(occ + j) < g + d) ++j;
-        if (j < b1 && (int64_t)__ldg(occ + j) == g + d) ++cnt;
+      if (dj == 0u) {
+        cnt = cnt0;
+      } else {
+        const uint32_t* j = ob;
+        for (const uint32_t* t = oa; t < oa_end; ++t) {  // cnt[d][a][b]: occurrences g of a with g + d holding b inside the read
+          const int64_t g = __ldg(t);
+          if (g + d > (int64_t)__ldg(unit_last + g)) continue;
+          while (j < ob_end && (int64_t)__ldg(j) < g + d) ++j;
+          if (j < ob_end && (int64_t)__ldg(j) == g + d) ++cnt;
+        }
       }
       if (cnt >= min_cov) {
         ++n_cand_d;
@@ -1789,10 +1859,16 @@ int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint
 int cfk_sketch_bits(void) { return SK_BITS; }
 int cfk_sketch_warps_per_block(void) { return SK_WARPS; }
 
+int64_t cfk_sketch_codes_elems(int64_t n_entries, int64_t n_units) {
+  if (n_entries < 0 || n_units < 0) return 0;
+  return (sk_block(n_entries, n_units) + 1) * SK_WINDOW;
+}
+
 int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, cfk_stream_t stream) {
   if (n_units < 0) return fail(CFK_ERR_INVALID, "cfk_sketch_codes: n_units < 0");
   if (n_units == 0) return CFK_OK;
-  sketch_codes_kernel<<<(unsigned)blocks_for(n_units, 8), 256, 0, (cudaStream_t)stream>>>(unit_ptr, ids, n_units, codes);
+  if (((uintptr_t)codes & 7u) != 0) return fail(CFK_ERR_INVALID, "cfk_sketch_codes: codes must be 8-byte aligned");
+  sketch_codes_kernel<<<(unsigned)blocks_for(n_units, 8), 256, 0, (cudaStream_t)stream>>>(unit_ptr, ids, n_units, (uint2*)codes);
   CFK_CHECK_LAUNCH("sketch_codes_kernel", 1);
   return CFK_OK;
 }
@@ -1803,6 +1879,7 @@ int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t
                     int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream) {
   if (n_entries < 0 || n_entries >= (1ll << 32))
     return fail(CFK_ERR_INVALID, "cfk_pair_sketch: need 0 <= n_entries < 2^32 (32-bit positions in the id array)");
+  if (((uintptr_t)codes & 7u) != 0) return fail(CFK_ERR_INVALID, "cfk_pair_sketch: codes must be 8-byte aligned");
   if (n_kmers < 0 || n_kmers >= (1ll << 32) - 1) return fail(CFK_ERR_INVALID, "cfk_pair_sketch: bad n_kmers");
   if (min_d < 0) return fail(CFK_ERR_INVALID, "cfk_pair_sketch: min_d < 0 is not defined by the reference loop");
   if (min_cov < CFK_SKETCH_MIN_COV || min_cov > CFK_SKETCH_MAX_COV)
@@ -1818,7 +1895,7 @@ int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t
     attr_done = true;
   }
   pair_sketch_kernel<<<(unsigned)n_blocks, SK_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      unit_ptr, ids, codes, unit_last, occ_ptr, occ, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
+      unit_ptr, ids, (const uint2*)codes, unit_last, occ_ptr, occ, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
       max_cand, counters);
   CFK_CHECK_LAUNCH("pair_sketch_kernel", 1);
   return CFK_OK;

@@ -383,7 +383,7 @@ class Engine:
         if self.pair_mode == "sketch" and not use_sketch:
             raise CfkError(f"pair_mode=sketch needs {SKETCH_MIN_COV} <= min_coverage <= {SKETCH_MAX_COV}")
         if use_sketch:
-            codes = self._empty(csr.n_entries, t.int16)
+            codes = self._empty(int(self.lib.cfk_sketch_codes_elems(csr.n_entries, csr.n_units)), t.int16)
             with self._stage("sketch_codes"):
                 _lib.call("cfk_sketch_codes", self._p(csr.unit_ptr), self._p(csr.ids), csr.n_units, self._p(codes),
                           self._stream())

@@ -44,7 +44,7 @@ extern "C" {
 #endif
 
 #ifndef CFK_SKETCH_BITS
-#define CFK_SKETCH_BITS 13        /* log2 of the byte counters in one warp's stage-C sketch (10..15) */
+#define CFK_SKETCH_BITS 13        /* log2 of the byte counters in one warp's stage-C sketch (10..13) */
 #endif
 #ifndef CFK_SKETCH_LOAD_DIV
 #define CFK_SKETCH_LOAD_DIV 4     /* a sketch pass is planned for <= 2^CFK_SKETCH_BITS / this many cloud entries */
@@ -191,10 +191,14 @@ int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint
  * sum_d cnt[d][a][b] -- and only ids whose counter reaches min_cov enter a small exact set that
  * is emitted.  The emitted pairs are a SUPERSET of the pairs whose chunk total reaches min_cov;
  * cfk_pair_join computes the exact counts either way, so the edges are identical.
- * codes = cfk_sketch_codes output: per cloud entry the hash of its id (low CFK_SKETCH_BITS
- * bits) and, in bit 15, whether another id of the same unit with the same hash precedes it. */
+ * codes = cfk_sketch_codes output, a buffer of cfk_sketch_codes_elems(n_entries, n_units) uint16
+ * (8-byte aligned) private to these two functions: per cloud entry the hash of its id (low
+ * CFK_SKETCH_BITS bits) and, in bit 15, whether another id of the same unit with the same hash
+ * precedes it, stored in 128-entry blocks per unit so that a lane fetches the four entries it
+ * serves in a step with one 8-byte load (the tail of a unit's last block is padding). */
 int cfk_sketch_bits(void);
 int cfk_sketch_warps_per_block(void);
+int64_t cfk_sketch_codes_elems(int64_t n_entries, int64_t n_units);
 int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, cfk_stream_t stream);
 int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* unit_last,
                     const int64_t* occ_ptr, const uint32_t* occ, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
