@@ -98,6 +98,7 @@ class Engine:
         self.n_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.cand_hint = 1 << 20
         self.edge_hint = 1 << 20
+        self.select_hint = {}  # (lo > 0, with_counts) -> output capacity that held last time
         self.table_load = 0.6  # distinct k-mers <= occurrences, so the stage-A table is at most this full
         # stage C kernel: "auto" = sketch where it applies, "exact" = always the exact tables, "sketch" = insist
         self.pair_mode = os.environ.get("CFK_PAIR_MODE", "auto")
@@ -235,17 +236,23 @@ class Engine:
     def table_select(self, table, lo, hi, max_nonuniq, with_counts=False, n_parts=0, part=0):
         """Compacted (keys[, n_reads, n_multi]) of slots inside the band, unordered."""
         t = self.torch
-        counters = self._counters()
         args = (self._p(table.slots), table.cap, int(lo), int(min(hi, U32_MAX)), int(min(max_nonuniq, U32_MAX)),
                 n_parts, part)
-        _lib.call("cfk_table_select", *args, None, None, None, 0, self._p(counters), self._stream())
-        n = int(counters.cpu()[0])
-        keys = self._empty(n, t.int64)
-        nreads = self._empty(n, t.int32) if with_counts else None
-        nmulti = self._empty(n, t.int32) if with_counts else None
-        counters.zero_()
-        _lib.call("cfk_table_select", *args, self._p(keys), self._p(nreads), self._p(nmulti), n,
-                  self._p(counters), self._stream())
+        hint_key = (int(lo) > 0, bool(with_counts))
+        max_out = int(self.select_hint.get(hint_key, 1 << 20))
+        while True:  # one pass over the table when the hint holds; a second one with the exact size otherwise
+            counters = self._counters()
+            keys = self._empty(max_out, t.int64)
+            nreads = self._empty(max_out, t.int32) if with_counts else None
+            nmulti = self._empty(max_out, t.int32) if with_counts else None
+            with self._stage("table_select"):
+                _lib.call("cfk_table_select", *args, self._p(keys), self._p(nreads), self._p(nmulti), max_out,
+                          self._p(counters), self._stream())
+            n = int(counters.cpu()[0])
+            if n <= max_out:
+                break
+            max_out = n
+        self.select_hint[hint_key] = max(max_out, int(n * 1.05) + 1024)
         if with_counts:
             return keys[:n], nreads[:n], nmulti[:n]
         return keys[:n]
