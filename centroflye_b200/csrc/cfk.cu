@@ -236,6 +236,208 @@ docfreq_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ 
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Stage A, resident form (the default): the work item is one (read, pass) instead of one read,
+// and the item's whole packed read is staged in shared memory next to the set.
+//   * every k-mer is rolled out of shared memory and every "is the k-mer stored at this slot
+//     mine?" check re-extracts the stored position's k-mer from shared memory, so phase 1 never
+//     leaves the SM and -- with no tile to restage -- the position loop has no barrier at all;
+//   * the passes of a long read (hash partitions of its k-mer space) are independent items, so
+//     a 300 kb read no longer serialises a dozen passes on one SM at the end of the kernel;
+//   * the shared memory is split per item: [ read words | set ], the set gets whatever the read
+//     leaves.  docfreq_plan_kernel computes the number of passes of every read from the same
+//     rule; the exclusive scan of those numbers (item_ptr) maps a ticket to (read, pass).
+// Reads too long to leave DF3_MIN_SET slots keep their words in global memory (same code, other
+// address space).
+// --------------------------------------------------------------------------------------------
+constexpr int DF3_SMEM_WORDS = 57344;  // 224 KB of dynamic shared memory
+constexpr int DF3_MIN_SET = 16384;
+
+struct Df3Geometry {
+  uint32_t n_words;   // words staged (0: the read stays in global memory)
+  uint32_t set_slots;
+  uint32_t fill;      // k-mers planned per pass
+};
+
+__host__ __device__ __forceinline__ Df3Geometry df3_geometry(int64_t len) {
+  Df3Geometry g;
+  const int64_t nw = (((len + 15) >> 4) + 3 + 3) & ~(int64_t)3;  // + the 3-word extraction window, multiple of 4
+  g.n_words = (nw <= DF3_SMEM_WORDS - DF3_MIN_SET) ? (uint32_t)nw : 0u;
+  g.set_slots = (uint32_t)DF3_SMEM_WORDS - g.n_words;
+  g.fill = (uint32_t)((uint64_t)g.set_slots * 53 / 100);
+  return g;
+}
+
+__global__ void docfreq_plan_kernel(const int64_t* __restrict__ read_len, const int32_t* __restrict__ order, int64_t n_reads,
+                                    int k, int32_t* __restrict__ n_pass) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_reads) return;
+  const int64_t len = read_len[order[i]], nk = len - k + 1;
+  int32_t np = 0;
+  if (nk > 0) {
+    const Df3Geometry g = df3_geometry(len);
+    np = (int32_t)((nk + g.fill - 1) / g.fill);
+  }
+  n_pass[i] = np;
+}
+
+template <bool IN_SMEM>
+__device__ __forceinline__ uint32_t df3_word(const uint32_t* words, uint32_t i) {
+  if (IN_SMEM) return words[i];
+  return __ldg(words + i);
+}
+
+// k-mer starting at base q; words[] must be readable up to word (q >> 4) + 2
+template <bool IN_SMEM>
+__device__ __forceinline__ uint64_t df3_kmer_at(const uint32_t* words, uint32_t q, int k) {
+  const uint32_t w = q >> 4, sh = (q & 15u) << 1;
+  uint64_t bits = ((uint64_t)df3_word<IN_SMEM>(words, w) | ((uint64_t)df3_word<IN_SMEM>(words, w + 1) << 32)) >> sh;
+  if (sh) bits |= (uint64_t)df3_word<IN_SMEM>(words, w + 2) << (64 - sh);
+  uint64_t r = __brevll(bits);
+  r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
+  return r >> (64 - 2 * k);
+}
+
+template <bool IN_SMEM>
+__device__ __forceinline__ void df3_item(const uint32_t* words, uint32_t* set, uint32_t c_eff, int64_t nk, int k,
+                                         uint32_t pass, uint32_t n_pass, uint64_t* table, int64_t cap, int64_t* counters) {
+  const uint64_t mask = (1ull << (2 * k)) - 1;
+  for (int64_t base = (int64_t)threadIdx.x * DF_PER_THREAD; base < nk; base += (int64_t)DF_THREADS * DF_PER_THREAD) {
+    const uint32_t p0 = (uint32_t)base;  // multiple of 8: sits at offset 0 or 8 of its word
+    const int npos = (int)min((int64_t)DF_PER_THREAD, nk - base);
+    // 48-base window starting at the word of p0; offset + 7 + k - 1 <= 8 + 7 + 30 < 48
+    const uint32_t w0 = p0 >> 4;
+    uint64_t win_lo = (uint64_t)df3_word<IN_SMEM>(words, w0) | ((uint64_t)df3_word<IN_SMEM>(words, w0 + 1) << 32);
+    uint32_t win_hi = df3_word<IN_SMEM>(words, w0 + 2);
+    if (p0 & 8u) {
+      win_lo = (win_lo >> 16) | ((uint64_t)win_hi << 48);
+      win_hi >>= 16;
+    }
+    // the first k - 1 bases in one go (reverse the 2-bit groups of the window), then roll
+    uint64_t kmer = 0;
+    const int s0 = 2 * (k - 1);
+    if (s0) {
+      uint64_t r = __brevll(win_lo);
+      r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);
+      kmer = r >> (64 - s0);
+      win_lo = (win_lo >> s0) | ((uint64_t)win_hi << (64 - s0));
+      win_hi = s0 < 32 ? (win_hi >> s0) : 0u;
+    }
+    uint64_t km[DF_PER_THREAD];
+    uint32_t act = 0;
+#pragma unroll
+    for (int j = 0; j < DF_PER_THREAD; ++j) {
+      kmer = ((kmer << 2) | (win_lo & 3u)) & mask;
+      win_lo = (win_lo >> 2) | ((uint64_t)win_hi << 62);
+      win_hi >>= 2;
+      km[j] = kmer;
+      if (j >= npos) continue;
+      if (n_pass > 1 && __umulhi((uint32_t)(kmer ^ (kmer >> 32)) * 0x9E3779B1u, n_pass) != pass) continue;
+      const uint32_t pos = p0 + (uint32_t)j;
+      uint32_t s = __umulhi((uint32_t)mix64(kmer), c_eff);
+      uint32_t probes = 0;
+      for (; probes < c_eff; ++probes) {
+        uint32_t v = ((volatile uint32_t*)set)[s];
+        if (v == 0) {
+          v = atomicCAS(set + s, 0u, pos + 1);
+          if (v == 0) {  // first sighting of this k-mer in this read
+            act |= 1u << (2 * j);
+            break;
+          }
+        }
+        if (df3_kmer_at<IN_SMEM>(words, (v & ~DF_MULTI) - 1, k) == kmer) {
+          if (!(v & DF_MULTI) && !(atomicOr(set + s, DF_MULTI) & DF_MULTI)) act |= 2u << (2 * j);  // exactly one thread flips the bit
+          break;
+        }
+        if (++s == c_eff) s = 0;
+      }
+      if (probes == c_eff) counters[1] = 1;  // cannot happen: a pass is planned for <= 53 % load
+    }
+    if (act == 0) continue;
+    // phase 2: the global table, four independent claims in flight per thread (see docfreq_kernel)
+#pragma unroll
+    for (int half = 0; half < DF_PER_THREAD / 4; ++half) {
+      if (((act >> (8 * half)) & 0xFFu) == 0) continue;
+      int64_t slot[4];
+      uint64_t old[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = half * 4 + j;
+        slot[j] = home_slot(mix64(km[jj]), cap);
+        old[j] = km[jj];
+        if ((act >> (2 * jj)) & 3u)
+          old[j] = atomicCAS((unsigned long long*)(table + 2 * slot[j]), (unsigned long long)EMPTY,
+                             (unsigned long long)km[jj]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = half * 4 + j;
+        const uint32_t what = (act >> (2 * jj)) & 3u;
+        if (!what) continue;
+        int64_t sl = slot[j];
+        if (old[j] != EMPTY && old[j] != km[jj]) sl = slot_upsert(table, cap, km[jj], sl + 1);
+        if (sl < 0) counters[0] = 1;
+        else atomicAdd(reinterpret_cast<uint32_t*>(table + 2 * sl + 1) + (what >> 1), 1u);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 1)
+docfreq_resident_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ read_off,
+                        const int64_t* __restrict__ read_len, const int32_t* __restrict__ order,
+                        const int64_t* __restrict__ item_ptr, int64_t n_reads, int k, uint64_t* table, int64_t cap,
+                        int64_t* counters) {
+  extern __shared__ __align__(16) uint32_t df_smem[];
+  __shared__ long long s_read;
+  __shared__ uint32_t s_pass, s_npass;
+  const int64_t n_items = item_ptr[n_reads];
+  for (;;) {
+    __syncthreads();  // previous item done with the shared memory and with s_*
+    if (threadIdx.x == 0) {
+      const int64_t t = (int64_t)atomicAdd((unsigned long long*)(counters + 2), 1ull);
+      long long idx = -1;
+      if (t < n_items) {
+        int64_t lo = 0, hi = n_reads;  // first j in (0, n_reads] with item_ptr[j] > t
+        while (hi - lo > 1) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (item_ptr[mid] > t) hi = mid; else lo = mid;
+        }
+        idx = lo;  // item_ptr[lo] <= t < item_ptr[lo + 1]
+        s_pass = (uint32_t)(t - item_ptr[idx]);
+        s_npass = (uint32_t)(item_ptr[idx + 1] - item_ptr[idx]);
+      }
+      s_read = idx;
+    }
+    __syncthreads();
+    const int64_t idx = s_read;
+    if (idx < 0) break;
+    const uint32_t pass = s_pass, n_pass = s_npass;
+    const int64_t r = order[idx];
+    const int64_t len = read_len[r], nk = len - k + 1;
+    const uint32_t* gwords = packed + (read_off[r] >> 4);  // every read starts on a 64-base boundary
+    const Df3Geometry g = df3_geometry(len);
+    uint32_t* set = df_smem + g.n_words;
+    const uint32_t c_eff = (n_pass > 1) ? g.set_slots : (uint32_t)min((int64_t)g.set_slots, max((int64_t)2048, (2 * nk + 3) & ~(int64_t)3));
+    for (uint32_t i = threadIdx.x * 4; i < c_eff; i += DF_THREADS * 4)  // n_words and c_eff are multiples of 4
+      *reinterpret_cast<uint4*>(set + i) = make_uint4(0, 0, 0, 0);
+    if (g.n_words) {
+      const uint32_t real_words = (uint32_t)((len + 15) >> 4);  // 16-byte loads stay inside the read's own 64-base blocks
+      const uint32_t real_quads = (real_words + 3) >> 2;
+      for (uint32_t i = threadIdx.x; i < g.n_words / 4; i += DF_THREADS) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (i < real_quads) v = __ldg(reinterpret_cast<const uint4*>(gwords) + i);
+        *reinterpret_cast<uint4*>(df_smem + 4 * i) = v;
+      }
+      __syncthreads();
+      df3_item<true>(df_smem, set, c_eff, nk, k, pass, n_pass, table, cap, counters);
+    } else {
+      __syncthreads();
+      df3_item<false>(gwords, set, c_eff, nk, k, pass, n_pass, table, cap, counters);
+    }
+  }
+}
+
 __global__ void table_init_kernel(uint64_t* table, int64_t cap) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cap) reinterpret_cast<ulonglong2*>(table)[i] = make_ulonglong2(EMPTY, 0ull);
@@ -1653,6 +1855,35 @@ int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int
   docfreq_kernel<<<(unsigned)n_blocks, DF_THREADS, smem, (cudaStream_t)stream>>>(packed, read_off, read_len, order, n_reads,
                                                                                k, table, cap, counters);
   CFK_CHECK_LAUNCH("docfreq_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_docfreq_plan(const int64_t* read_len, const int32_t* order, int64_t n_reads, int k, int32_t* n_pass,
+                     cfk_stream_t stream) {
+  if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_docfreq_plan: k must be in [1, 31]");
+  if (n_reads < 0) return fail(CFK_ERR_INVALID, "cfk_docfreq_plan: bad sizes");
+  if (n_reads == 0) return CFK_OK;
+  docfreq_plan_kernel<<<(unsigned)blocks_for(n_reads, 256), 256, 0, (cudaStream_t)stream>>>(read_len, order, n_reads, k, n_pass);
+  CFK_CHECK_LAUNCH("docfreq_plan_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len,
+                               const int32_t* order, const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* table,
+                               int64_t cap, int64_t* counters, int32_t n_blocks, cfk_stream_t stream) {
+  if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_docfreq_count_resident: k must be in [1, 31]");
+  if (cap < 1 || n_reads < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_docfreq_count_resident: bad sizes");
+  if (n_reads == 0) return CFK_OK;
+  static bool attr_done = false;
+  const int smem = DF3_SMEM_WORDS * 4;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(docfreq_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_docfreq_count_resident: cudaFuncSetAttribute", e);
+    attr_done = true;
+  }
+  docfreq_resident_kernel<<<(unsigned)n_blocks, DF_THREADS, smem, (cudaStream_t)stream>>>(
+      packed, read_off, read_len, order, item_ptr, n_reads, k, table, cap, counters);
+  CFK_CHECK_LAUNCH("docfreq_resident_kernel", 1);
   return CFK_OK;
 }
 

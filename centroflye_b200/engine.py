@@ -102,6 +102,10 @@ class Engine:
         self.table_load = 0.6  # distinct k-mers <= occurrences, so the stage-A table is at most this full
         # stage C kernel: "auto" = sketch where it applies, "exact" = always the exact tables, "sketch" = insist
         self.pair_mode = os.environ.get("CFK_PAIR_MODE", "auto")
+        # stage A kernel: "resident" = (read, pass) items with the read staged in shared memory, "tiled" = one block per read
+        self.docfreq_mode = os.environ.get("CFK_DOCFREQ_MODE", "resident")
+        if self.docfreq_mode not in ("resident", "tiled"):
+            raise CfkError(f"CFK_DOCFREQ_MODE must be resident or tiled, got {self.docfreq_mode!r}")
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
         self._host_pool = {}  # name -> pinned uint8 buffer for results (to_host)
 
@@ -219,13 +223,24 @@ class Engine:
         k = check_k(k)
         total_k = n_kmers_hint if n_kmers_hint is not None else max(reads.n_bases - reads.n_reads * (k - 1), 0)
         cap = max(1024, int(total_k / self.table_load) + 1)
+        item_ptr = None
+        if self.docfreq_mode == "resident" and reads.n_reads:
+            n_pass = self._empty(reads.n_reads, self.torch.int32)
+            _lib.call("cfk_docfreq_plan", self._p(reads.read_len), self._p(reads.order), reads.n_reads, k,
+                      self._p(n_pass), self._stream())
+            item_ptr = self.exclusive_scan(n_pass[:reads.n_reads])
         while True:
             table = self.new_table(cap)
             counters = self._counters()
             with self._stage("docfreq"):
-                _lib.call("cfk_docfreq_count", self._p(reads.packed), self._p(reads.read_off),
-                          self._p(reads.read_len), self._p(reads.order), reads.n_reads, k, self._p(table.slots), cap,
-                          self._p(counters), self.n_sms, self._stream())
+                if item_ptr is not None:
+                    _lib.call("cfk_docfreq_count_resident", self._p(reads.packed), self._p(reads.read_off),
+                              self._p(reads.read_len), self._p(reads.order), self._p(item_ptr), reads.n_reads, k,
+                              self._p(table.slots), cap, self._p(counters), self.n_sms, self._stream())
+                else:
+                    _lib.call("cfk_docfreq_count", self._p(reads.packed), self._p(reads.read_off),
+                              self._p(reads.read_len), self._p(reads.order), reads.n_reads, k, self._p(table.slots),
+                              cap, self._p(counters), self.n_sms, self._stream())
             c = counters.cpu()
             if int(c[1]):
                 raise CfkError("stage A: per-read k-mer set overflowed (internal error)")

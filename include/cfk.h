@@ -82,6 +82,20 @@ int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int
                       int64_t n_reads, int k, uint64_t* table, int64_t cap, int64_t* counters, int32_t n_blocks,
                       cfk_stream_t stream);
 
+/* Resident form of cfk_docfreq_count (the default path; same results, same table, same counters).
+ * The work item is one (read, pass): a pass is a hash partition of the read's k-mer space small
+ * enough for the per-read set, and the whole packed read is staged in shared memory beside the
+ * set (224 KB: [read words | set]), so the per-read de-duplication of
+ * distance_based_kmer_recruitment.py:50-53 never leaves the SM and the passes of a long read
+ * run on different SMs.  cfk_docfreq_plan writes n_pass[i] = passes of read order[i]; the caller
+ * turns it into item_ptr[n_reads + 1] with cfk_exclusive_scan and hands that to
+ * cfk_docfreq_count_resident.  Reads of more than ~655 kb keep their words in global memory. */
+int cfk_docfreq_plan(const int64_t* read_len, const int32_t* order, int64_t n_reads, int k, int32_t* n_pass,
+                     cfk_stream_t stream);
+int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len,
+                               const int32_t* order, const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* table,
+                               int64_t cap, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
+
 /* Merge (key, n_reads, n_multi) records counted elsewhere (another GPU's shard) into a table:
  * the owner-side half of the multi-GPU all-to-all.  counters[0] != 0: full. */
 int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n, uint64_t* table,

@@ -248,3 +248,41 @@ def test_table_partition_matches_owner_rule(eng):
         assert np.array_equal(got_k[order], keys)
         assert np.array_equal(r_.cpu().numpy().view(np.uint32)[order], nr)
         assert np.array_equal(m_.cpu().numpy().view(np.uint32)[order], nm)
+
+
+@pytest.fixture(params=["resident", "tiled"])
+def docfreq_mode(eng, request):
+    """Both stage-A kernels: (read, pass) items with the read resident in shared memory, and one block per read."""
+    old, eng.docfreq_mode = eng.docfreq_mode, request.param
+    yield request.param
+    eng.docfreq_mode = old
+
+
+def _repetitive_read(rng, length, unit_len, div):
+    unit = rng.integers(0, 4, size=unit_len, dtype=np.uint8)
+    out = np.tile(unit, length // unit_len + 1)[:length].copy()
+    flip = rng.random(length) < div
+    out[flip] = rng.integers(0, 4, size=int(flip.sum()), dtype=np.uint8)
+    return out
+
+
+@pytest.mark.parametrize("k", [1, 5, 19, 31])
+def test_docfreq_read_shapes(eng, docfreq_mode, k):
+    """Stage A on reads of every shape the kernels treat differently: shorter than k, exactly k, one set pass,
+    several passes (> 29 k k-mers), too long to stay resident in shared memory (> 655 kb), all highly repetitive
+    (so n_multi matters) -- against the C restatement of dbkr.py:39-63."""
+    from centroflye_b200.ingest import pack_reads
+    from oracle import c_oracle
+    rng = np.random.default_rng(100 + k)
+    lens = [0, k - 1, k, k + 1, 63, 64, 65, 1000, 8191, 8192, 8200, 29000, 31000, 70001, 131072, 300000, 700000, 5000, 5000]
+    codes = [_repetitive_read(rng, max(n, 0), int(rng.integers(20, 400)), 0.02) for n in lens]
+    codes[-1] = codes[-2].copy()  # the same read twice: n_reads 2, n_multi per read as before
+    batch = pack_reads(codes, [f"r{i}" for i in range(len(codes))])
+    table = eng.count_docfreq(eng.upload_reads(batch, k), k)
+    keys, nr, nm = eng.table_select(table, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)
+    keys = keys.cpu().numpy().view(np.uint64)
+    order = np.argsort(keys)
+    wk, wr, wm = c_oracle.docfreq(c_oracle.unpacked_codes(batch), batch, k)
+    assert np.array_equal(keys[order], wk)
+    assert np.array_equal(nr.cpu().numpy().view(np.uint32)[order], wr)
+    assert np.array_equal(nm.cpu().numpy().view(np.uint32)[order], wm)
