@@ -51,6 +51,17 @@ SIGNATURES = {
                                _i32, _p]),
     "cfk_pair_join": (_int, [_p, _i64, _p, _p, _p, _i32, _i32, _u32, _f64, _p, _i64, _p, _p, _p]),
     "cfk_flag_indices": (_int, [_p, _i64, _p, _p, _p]),
+    # native NCRF ingestion (host pointers)
+    "cfk_ncrf_last_error": (ctypes.c_char_p, []),
+    "cfk_ncrf_open": (_int, [ctypes.c_char_p, _i64, _i32, _i32, ctypes.POINTER(_p)]),
+    "cfk_ncrf_n_records": (_i64, [_p]),
+    "cfk_ncrf_n_seen": (_i64, [_p]),
+    "cfk_ncrf_n_words": (_i64, [_p]),
+    "cfk_ncrf_n_bases": (_i64, [_p]),
+    "cfk_ncrf_n_units": (_i64, [_p]),
+    "cfk_ncrf_ids_bytes": (_i64, [_p]),
+    "cfk_ncrf_export": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "cfk_ncrf_close": (None, [_p]),
 }
 
 _lib = None

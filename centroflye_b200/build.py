@@ -6,11 +6,13 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "cfk.cu")
+INGEST_SRC = os.path.join(HERE, "csrc", "ncrf_ingest.cpp")  # host-side NCRF ingestion, same library
+SOURCES = [SRC, INGEST_SRC]
 HDR = os.path.join(os.path.dirname(HERE), "include", "cfk.h")
 OUT = os.path.join(HERE, "libcfk.so")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC,-pthread"]
 
 
 def nvcc_path():
@@ -21,19 +23,29 @@ def nvcc_path():
 
 
 def up_to_date():
-    return os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(SRC), os.path.getmtime(HDR))
+    return os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(HDR), *(os.path.getmtime(p) for p in SOURCES))
 
 
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SOURCES
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
     return OUT
+
+
+def build_variant(tag, defines):
+    """Tuning experiments: gpurun_tmp_libcfk_<tag>.so at the repo root with extra -D flags (loaded via CFK_LIBRARY)."""
+    out = os.path.join(os.path.dirname(HERE), f"gpurun_tmp_libcfk_{tag}.so")
+    cmd = [nvcc_path()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + SOURCES
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return out
 
 
 if __name__ == "__main__":

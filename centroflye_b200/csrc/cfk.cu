@@ -252,6 +252,14 @@ docfreq_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ 
 // --------------------------------------------------------------------------------------------
 constexpr int DF3_SMEM_WORDS = 57344;  // 224 KB of dynamic shared memory
 constexpr int DF3_MIN_SET = 16384;
+#ifndef CFK_DF3_FILL_PCT
+#define CFK_DF3_FILL_PCT 53   /* planned load of the per-read set, percent */
+#endif
+#ifndef CFK_DF3_PER_THREAD
+#define CFK_DF3_PER_THREAD 4  /* consecutive k-mer starts per lane and grab (4 or 8) */
+#endif
+constexpr int DF3_PER_THREAD = CFK_DF3_PER_THREAD;
+static_assert(DF3_PER_THREAD == 4 || DF3_PER_THREAD == 8, "the window holds 8 + 7 + 30 bases; claims go in groups of 4");
 
 struct Df3Geometry {
   uint32_t n_words;   // words staged (0: the read stays in global memory)
@@ -264,7 +272,7 @@ __host__ __device__ __forceinline__ Df3Geometry df3_geometry(int64_t len) {
   const int64_t nw = (((len + 15) >> 4) + 3 + 3) & ~(int64_t)3;  // + the 3-word extraction window, multiple of 4
   g.n_words = (nw <= DF3_SMEM_WORDS - DF3_MIN_SET) ? (uint32_t)nw : 0u;
   g.set_slots = (uint32_t)DF3_SMEM_WORDS - g.n_words;
-  g.fill = (uint32_t)((uint64_t)g.set_slots * 53 / 100);
+  g.fill = (uint32_t)((uint64_t)g.set_slots * CFK_DF3_FILL_PCT / 100);
   return g;
 }
 
@@ -298,20 +306,48 @@ __device__ __forceinline__ uint64_t df3_kmer_at(const uint32_t* words, uint32_t 
   return r >> (64 - 2 * k);
 }
 
+// hash of a k-mer for the per-read set: the pass partition takes the top bits of f * golden, the slot and the
+// fingerprint come from a second, independent mix of the same folded value
+__device__ __forceinline__ uint32_t df3_fold(uint64_t kmer) { return (uint32_t)(kmer ^ (kmer >> 32)); }
+__device__ __forceinline__ uint32_t df3_mix(uint32_t f) {
+  uint32_t g = f * 0x85EBCA6Bu;
+  g ^= g >> 13;
+  g *= 0xC2B2AE35u;
+  g ^= g >> 16;
+  return g;
+}
+
+constexpr int DF3_CHUNK = 32 * DF3_PER_THREAD;  // k-mer starts one warp takes per grab
+
+// Set slot (32 bit): bit 31 = "seen again", bits [pos_bits - 1 : 0] = position of the first occurrence + 1 (0 = empty),
+// bits [30 : pos_bits] = fingerprint of the k-mer, so that most foreign slots of a probe chain are skipped without
+// re-extracting their k-mer.
 template <bool IN_SMEM>
 __device__ __forceinline__ void df3_item(const uint32_t* words, uint32_t* set, uint32_t c_eff, int64_t nk, int k,
-                                         uint32_t pass, uint32_t n_pass, uint64_t* table, int64_t cap, int64_t* counters) {
+                                         uint32_t pass, uint32_t n_pass, uint64_t* table, int64_t cap, int64_t* counters,
+                                         uint32_t* s_chunk) {
   const uint64_t mask = (1ull << (2 * k)) - 1;
-  for (int64_t base = (int64_t)threadIdx.x * DF_PER_THREAD; base < nk; base += (int64_t)DF_THREADS * DF_PER_THREAD) {
-    const uint32_t p0 = (uint32_t)base;  // multiple of 8: sits at offset 0 or 8 of its word
-    const int npos = (int)min((int64_t)DF_PER_THREAD, nk - base);
-    // 48-base window starting at the word of p0; offset + 7 + k - 1 <= 8 + 7 + 30 < 48
+  const int lane = threadIdx.x & 31;
+  const int pos_bits = 64 - __clzll((unsigned long long)nk);  // pos + 1 <= nk fits
+  const uint32_t pos_mask = pos_bits >= 31 ? 0x7FFFFFFFu : ((1u << pos_bits) - 1u);
+  const uint32_t fp_mask = 0x7FFFFFFFu & ~pos_mask;
+  for (;;) {
+    uint32_t chunk = 0;
+    if (lane == 0) chunk = atomicAdd(s_chunk, 1u);
+    chunk = __shfl_sync(FULL, chunk, 0);
+    const int64_t chunk0 = (int64_t)chunk * DF3_CHUNK;
+    if (chunk0 >= nk) break;
+    const int64_t base = chunk0 + lane * DF3_PER_THREAD;
+    if (base >= nk) continue;
+    const uint32_t p0 = (uint32_t)base;  // multiple of 4: sits at offset 0, 4, 8 or 12 of its word
+    const int npos = (int)min((int64_t)DF3_PER_THREAD, nk - base);
+    // 48-base window starting at the word of p0; offset + DF3_PER_THREAD - 1 + k - 1 <= 45 < 48 (12 + 3 + 30 or 8 + 7 + 30)
     const uint32_t w0 = p0 >> 4;
     uint64_t win_lo = (uint64_t)df3_word<IN_SMEM>(words, w0) | ((uint64_t)df3_word<IN_SMEM>(words, w0 + 1) << 32);
     uint32_t win_hi = df3_word<IN_SMEM>(words, w0 + 2);
-    if (p0 & 8u) {
-      win_lo = (win_lo >> 16) | ((uint64_t)win_hi << 48);
-      win_hi >>= 16;
+    if (const uint32_t sh0 = (p0 & 15u) << 1) {
+      win_lo = (win_lo >> sh0) | ((uint64_t)win_hi << (64 - sh0));
+      win_hi >>= sh0;
     }
     // the first k - 1 bases in one go (reverse the 2-bit groups of the window), then roll
     uint64_t kmer = 0;
@@ -323,29 +359,32 @@ __device__ __forceinline__ void df3_item(const uint32_t* words, uint32_t* set, u
       win_lo = (win_lo >> s0) | ((uint64_t)win_hi << (64 - s0));
       win_hi = s0 < 32 ? (win_hi >> s0) : 0u;
     }
-    uint64_t km[DF_PER_THREAD];
+    uint64_t km[DF3_PER_THREAD];
     uint32_t act = 0;
 #pragma unroll
-    for (int j = 0; j < DF_PER_THREAD; ++j) {
+    for (int j = 0; j < DF3_PER_THREAD; ++j) {
       kmer = ((kmer << 2) | (win_lo & 3u)) & mask;
       win_lo = (win_lo >> 2) | ((uint64_t)win_hi << 62);
       win_hi >>= 2;
       km[j] = kmer;
       if (j >= npos) continue;
-      if (n_pass > 1 && __umulhi((uint32_t)(kmer ^ (kmer >> 32)) * 0x9E3779B1u, n_pass) != pass) continue;
-      const uint32_t pos = p0 + (uint32_t)j;
-      uint32_t s = __umulhi((uint32_t)mix64(kmer), c_eff);
+      const uint32_t f = df3_fold(kmer);
+      if (n_pass > 1 && __umulhi(f * 0x9E3779B1u, n_pass) != pass) continue;
+      const uint32_t g = df3_mix(f);
+      const uint32_t mine = (g << pos_bits) & fp_mask;  // pos_bits <= 31
+      const uint32_t fresh = (p0 + (uint32_t)j + 1u) | mine;
+      uint32_t s = __umulhi(g, c_eff);
       uint32_t probes = 0;
       for (; probes < c_eff; ++probes) {
         uint32_t v = ((volatile uint32_t*)set)[s];
         if (v == 0) {
-          v = atomicCAS(set + s, 0u, pos + 1);
+          v = atomicCAS(set + s, 0u, fresh);
           if (v == 0) {  // first sighting of this k-mer in this read
             act |= 1u << (2 * j);
             break;
           }
         }
-        if (df3_kmer_at<IN_SMEM>(words, (v & ~DF_MULTI) - 1, k) == kmer) {
+        if (((v ^ mine) & fp_mask) == 0 && df3_kmer_at<IN_SMEM>(words, (v & pos_mask) - 1u, k) == kmer) {
           if (!(v & DF_MULTI) && !(atomicOr(set + s, DF_MULTI) & DF_MULTI)) act |= 2u << (2 * j);  // exactly one thread flips the bit
           break;
         }
@@ -356,7 +395,7 @@ __device__ __forceinline__ void df3_item(const uint32_t* words, uint32_t* set, u
     if (act == 0) continue;
     // phase 2: the global table, four independent claims in flight per thread (see docfreq_kernel)
 #pragma unroll
-    for (int half = 0; half < DF_PER_THREAD / 4; ++half) {
+    for (int half = 0; half < DF3_PER_THREAD / 4; ++half) {
       if (((act >> (8 * half)) & 0xFFu) == 0) continue;
       int64_t slot[4];
       uint64_t old[4];
@@ -383,42 +422,46 @@ __device__ __forceinline__ void df3_item(const uint32_t* words, uint32_t* set, u
   }
 }
 
+// ticket -> (index into order[], pass, passes of that read); index -1 when the items are used up
+__device__ __forceinline__ void df3_fetch(const int64_t* __restrict__ item_ptr, int64_t n_reads, int64_t n_items,
+                                          int64_t* counters, long long* s_read, uint32_t* s_pass, uint32_t* s_npass) {
+  const int64_t t = (int64_t)atomicAdd((unsigned long long*)(counters + 2), 1ull);
+  long long idx = -1;
+  if (t < n_items) {
+    int64_t lo = 0, hi = n_reads;  // item_ptr[lo] <= t < item_ptr[hi]
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(item_ptr + mid) > t) hi = mid; else lo = mid;
+    }
+    idx = lo;
+    const int64_t first = __ldg(item_ptr + lo);
+    *s_pass = (uint32_t)(t - first);
+    *s_npass = (uint32_t)(__ldg(item_ptr + lo + 1) - first);
+  }
+  *s_read = idx;
+}
+
 __global__ void __launch_bounds__(DF_THREADS, 1)
 docfreq_resident_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ read_off,
                         const int64_t* __restrict__ read_len, const int32_t* __restrict__ order,
                         const int64_t* __restrict__ item_ptr, int64_t n_reads, int k, uint64_t* table, int64_t cap,
                         int64_t* counters) {
   extern __shared__ __align__(16) uint32_t df_smem[];
-  __shared__ long long s_read;
-  __shared__ uint32_t s_pass, s_npass;
-  const int64_t n_items = item_ptr[n_reads];
-  for (;;) {
-    __syncthreads();  // previous item done with the shared memory and with s_*
-    if (threadIdx.x == 0) {
-      const int64_t t = (int64_t)atomicAdd((unsigned long long*)(counters + 2), 1ull);
-      long long idx = -1;
-      if (t < n_items) {
-        int64_t lo = 0, hi = n_reads;  // first j in (0, n_reads] with item_ptr[j] > t
-        while (hi - lo > 1) {
-          const int64_t mid = (lo + hi) >> 1;
-          if (item_ptr[mid] > t) hi = mid; else lo = mid;
-        }
-        idx = lo;  // item_ptr[lo] <= t < item_ptr[lo + 1]
-        s_pass = (uint32_t)(t - item_ptr[idx]);
-        s_npass = (uint32_t)(item_ptr[idx + 1] - item_ptr[idx]);
-      }
-      s_read = idx;
-    }
-    __syncthreads();
-    const int64_t idx = s_read;
+  __shared__ long long s_read[2];
+  __shared__ uint32_t s_pass[2], s_npass[2], s_chunk;
+  const int64_t n_items = __ldg(item_ptr + n_reads);
+  if (threadIdx.x == 0) df3_fetch(item_ptr, n_reads, n_items, counters, &s_read[0], &s_pass[0], &s_npass[0]);
+  for (int cur = 0;; cur ^= 1) {
+    __syncthreads();  // item `cur` is published; everybody is done with the previous item's shared memory
+    const int64_t idx = s_read[cur];
     if (idx < 0) break;
-    const uint32_t pass = s_pass, n_pass = s_npass;
+    const uint32_t pass = s_pass[cur], n_pass = s_npass[cur];
     const int64_t r = order[idx];
     const int64_t len = read_len[r], nk = len - k + 1;
     const uint32_t* gwords = packed + (read_off[r] >> 4);  // every read starts on a 64-base boundary
     const Df3Geometry g = df3_geometry(len);
     uint32_t* set = df_smem + g.n_words;
-    const uint32_t c_eff = (n_pass > 1) ? g.set_slots : (uint32_t)min((int64_t)g.set_slots, max((int64_t)2048, (2 * nk + 3) & ~(int64_t)3));
+    const uint32_t c_eff = (n_pass > 1) ? g.set_slots : (uint32_t)min((int64_t)g.set_slots, max((int64_t)2048, (nk * 100 / CFK_DF3_FILL_PCT + 7) & ~(int64_t)3));
     for (uint32_t i = threadIdx.x * 4; i < c_eff; i += DF_THREADS * 4)  // n_words and c_eff are multiples of 4
       *reinterpret_cast<uint4*>(set + i) = make_uint4(0, 0, 0, 0);
     if (g.n_words) {
@@ -429,12 +472,13 @@ docfreq_resident_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
         if (i < real_quads) v = __ldg(reinterpret_cast<const uint4*>(gwords) + i);
         *reinterpret_cast<uint4*>(df_smem + 4 * i) = v;
       }
-      __syncthreads();
-      df3_item<true>(df_smem, set, c_eff, nk, k, pass, n_pass, table, cap, counters);
-    } else {
-      __syncthreads();
-      df3_item<false>(gwords, set, c_eff, nk, k, pass, n_pass, table, cap, counters);
     }
+    if (threadIdx.x == 0) s_chunk = 0;
+    __syncthreads();
+    // the next item's ticket and its search run behind the other warps' work on this one
+    if (threadIdx.x == 0) df3_fetch(item_ptr, n_reads, n_items, counters, &s_read[cur ^ 1], &s_pass[cur ^ 1], &s_npass[cur ^ 1]);
+    if (g.n_words) df3_item<true>(df_smem, set, c_eff, nk, k, pass, n_pass, table, cap, counters, &s_chunk);
+    else df3_item<false>(gwords, set, c_eff, nk, k, pass, n_pass, table, cap, counters, &s_chunk);
   }
 }
 

@@ -129,3 +129,44 @@ def batch_from_synth(reads, motif_len, min_record_len=5000):
         bounds.append(b)
     batch = pack_reads(codes, kept)
     return batch, units_from_boundaries(batch, bounds)
+
+
+def native_ingest(report_fn, n=1, min_record_len=5000, threads=0):
+    """NCRF report file -> (ReadBatch, UnitIndex, fields) in one native pass (libcfk.so, csrc/ncrf_ingest.cpp).
+
+    Equal, array for array, to ``batch_from_report(NCRF_Report(fn))`` + ``units_from_report(report, batch, n)``
+    (tests/test_ncrf_native.py), without a Python object or string per record.  ``fields`` is an int64 array
+    [R, 8]: r_len, r_al_len, r_st, r_en, strand (+1/-1), m_al_len, score, alignment columns — the scalar
+    attributes of the reference's NCRF_Record (scripts/ncrf_parser.py:13-26) after the strand flip (:96-100).
+    Raises ValueError on what makes the Python path raise (dangling line, malformed record, non-ACGT symbol)."""
+    import ctypes
+    import os
+    from . import _lib
+    lib = _lib.load()
+    ctx = ctypes.c_void_p()
+    rc = lib.cfk_ncrf_open(os.fsencode(report_fn), int(min_record_len), int(n), int(threads), ctypes.byref(ctx))
+    if rc != 0:
+        msg = lib.cfk_ncrf_last_error().decode(errors="replace")
+        if "cannot open" in msg:
+            raise FileNotFoundError(msg)
+        raise ValueError(msg)
+    try:
+        R, U = int(lib.cfk_ncrf_n_records(ctx)), int(lib.cfk_ncrf_n_units(ctx))
+        packed = np.empty(int(lib.cfk_ncrf_n_words(ctx)), dtype=np.uint32)
+        read_off, read_len = np.empty(R, dtype=np.int64), np.empty(R, dtype=np.int64)
+        ptr = np.empty(R + 1, dtype=np.int64)
+        unit_off, unit_len = np.empty(U, dtype=np.int64), np.empty(U, dtype=np.int32)
+        unit_read = np.empty(U, dtype=np.int32)
+        ids = np.empty(max(int(lib.cfk_ncrf_ids_bytes(ctx)), 1), dtype=np.uint8)
+        fields = np.empty((R, 8), dtype=np.int64)
+        rc = lib.cfk_ncrf_export(ctx, packed.ctypes.data, read_off.ctypes.data, read_len.ctypes.data, ptr.ctypes.data,
+                                 unit_off.ctypes.data, unit_len.ctypes.data, unit_read.ctypes.data, ids.ctypes.data,
+                                 fields.ctypes.data)
+        if rc != 0:
+            raise ValueError(lib.cfk_ncrf_last_error().decode(errors="replace"))
+        n_bases = int(lib.cfk_ncrf_n_bases(ctx))
+    finally:
+        lib.cfk_ncrf_close(ctx)
+    r_ids = ids.tobytes()[: int(ids.size) if R else 0].decode("utf-8", errors="replace").split("\n")[:R]
+    batch = ReadBatch(r_ids=r_ids, packed=packed, read_off=read_off, read_len=read_len, n_bases=n_bases)
+    return batch, UnitIndex(read_unit_ptr=ptr, unit_off=unit_off, unit_len=unit_len, unit_read=unit_read), fields

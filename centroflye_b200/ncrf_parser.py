@@ -97,6 +97,7 @@ class NCRF_Report:
 
     def __init__(self, report_fn, min_record_len=5000):
         self.records = {}
+        self._cfk_source = (report_fn, min_record_len)  # lets the device path ingest the file natively (ingest.native_ingest)
         self.positions_all_alignments = defaultdict(list)
         self.read_lens = {}
         with open(report_fn, "r") as f:

@@ -119,17 +119,41 @@ def _report_cache(report):
     return cache
 
 
+def _native(report, n):
+    """(ReadBatch, UnitIndex) of the report's file through the native ingestion, or None when the report object was
+    not built from a file or no longer matches it (records added / removed by the caller)."""
+    src = getattr(report, "_cfk_source", None)
+    if src is None:
+        return None
+    from .ingest import native_ingest
+    try:
+        batch, units, _ = native_ingest(src[0], n=n, min_record_len=src[1])
+    except (OSError, ValueError):
+        return None  # the Python path below raises the reference-shaped error, if any
+    if batch.r_ids != list(report.records.keys()):
+        return None
+    return batch, units
+
+
 def report_batch(report):
     cache = _report_cache(report)
     if "batch" not in cache:
-        cache["batch"] = batch_from_report(report)
+        got = _native(report, 1)
+        if got is not None:
+            cache["batch"], cache["units"][1] = got
+        else:
+            cache["batch"] = batch_from_report(report)
     return cache["batch"]
 
 
 def report_units(report, n):
     cache = _report_cache(report)
     if n not in cache["units"]:
-        cache["units"][n] = units_from_report(report, report_batch(report), n=n)
+        got = _native(report, n) if getattr(report, "_cfk_source", None) is not None else None
+        if got is not None and np.array_equal(got[0].read_off, report_batch(report).read_off):
+            cache["units"][n] = got[1]
+        else:
+            cache["units"][n] = units_from_report(report, report_batch(report), n=n)
     return cache["units"][n]
 
 

@@ -234,6 +234,40 @@ int cfk_pair_join(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, 
 /* Indices of non-zero flags, ascending (the recruited k-mer ids).  counters[0] zeroed. */
 int cfk_flag_indices(const uint8_t* flags, int64_t n, uint32_t* out, int64_t* counters, cfk_stream_t stream);
 
+/* ---- native NCRF ingestion (host code) --------------------------------
+ * One pass from the report text to the flat host arrays the device consumes, replacing the
+ * per-record Python of NCRF_Report.__init__ (scripts/ncrf_parser.py:61-118: 2-line records, '#'
+ * and blank lines dropped, longest alignment per read id kept if r_al_len >= min_record_len,
+ * '-' strand rows reverse-complemented with utils/bio.py:27-29), of the gap removal in
+ * distance_based_kmer_recruitment.py:47 / read_kmer_cloud.py:25, and of the unit segmentation
+ * get_motif_alignments(n) (scripts/ncrf_parser.py:28-59: non-overlapping leftmost matches of
+ * motif * n in the gap-free upper-cased motif row, partial first / last unit kept when longer
+ * than 0.2 * len(motif)).  All pointers are HOST pointers (numpy / pinned torch buffers).
+ *
+ * cfk_ncrf_open parses, selects and segments (n_threads <= 0: all cores) into an opaque context;
+ * the size queries tell the caller how much to allocate; cfk_ncrf_export writes
+ *   packed_h[n_words]        2-bit packed gap-free reads, every read on a 64-base boundary,
+ *   read_off_h / read_len_h [n_records],  read_unit_ptr_h [n_records + 1],
+ *   unit_off_h / unit_len_h / unit_read_h [n_units]   (may be NULL),
+ *   ids_h [ids_bytes]        record ids in dict order, '\n' after each        (may be NULL),
+ *   fields_h [8 * n_records] r_len, r_al_len, r_st, r_en, strand (+1 / -1), m_al_len, score,
+ *                            alignment columns                               (may be NULL);
+ * a symbol outside upper-case ACGT in a read row is an error (CFK_ERR_INVALID), as in the Python
+ * host path.  cfk_ncrf_close frees the context.  Errors: cfk_ncrf_last_error(). */
+typedef struct cfk_ncrf cfk_ncrf_t;
+const char* cfk_ncrf_last_error(void);
+int cfk_ncrf_open(const char* path, int64_t min_record_len, int32_t n_per_match, int32_t n_threads, cfk_ncrf_t** out);
+int64_t cfk_ncrf_n_records(const cfk_ncrf_t* ctx);
+int64_t cfk_ncrf_n_seen(const cfk_ncrf_t* ctx);
+int64_t cfk_ncrf_n_words(const cfk_ncrf_t* ctx);
+int64_t cfk_ncrf_n_bases(const cfk_ncrf_t* ctx);
+int64_t cfk_ncrf_n_units(const cfk_ncrf_t* ctx);
+int64_t cfk_ncrf_ids_bytes(const cfk_ncrf_t* ctx);
+int cfk_ncrf_export(const cfk_ncrf_t* ctx, uint32_t* packed_h, int64_t* read_off_h, int64_t* read_len_h,
+                    int64_t* read_unit_ptr_h, int64_t* unit_off_h, int32_t* unit_len_h, int32_t* unit_read_h,
+                    char* ids_h, int64_t* fields_h);
+void cfk_ncrf_close(cfk_ncrf_t* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ def sass_lines(so_path, kernel):
     with tempfile.TemporaryDirectory() as tmp:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so_path)], cwd=tmp, check=True,
                        capture_output=True)
-        cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+        cubin = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))
         text = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True,
                               text=True).stdout
     out, inside, cur = [], False, None
