@@ -40,6 +40,7 @@ SIGNATURES = {
     "cfk_cloud_filter_write": (_int, [_p, _p, _i64, _p, _i64, _i64, _p, _p, _p]),
     "cfk_occ_fill": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p]),
     "cfk_occ_sort": (_int, [_p, _p, _i64, _p]),
+    "cfk_occ_last": (_int, [_p, _i64, _p, _p, _p]),
     "cfk_unit_splits": (_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
     "cfk_pair_candidates": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p,
                                    _i32, _p]),
@@ -47,9 +48,9 @@ SIGNATURES = {
     "cfk_sketch_warps_per_block": (_int, []),
     "cfk_sketch_codes_elems": (_i64, [_i64, _i64]),
     "cfk_sketch_codes": (_int, [_p, _p, _i64, _p, _p]),
-    "cfk_pair_sketch": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p,
+    "cfk_pair_sketch": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p,
                                _i32, _p]),
-    "cfk_pair_join": (_int, [_p, _i64, _p, _p, _p, _i32, _i32, _u32, _f64, _p, _i64, _p, _p, _p]),
+    "cfk_pair_join": (_int, [_p, _i64, _p, _p, _p, _p, _i32, _i32, _u32, _f64, _p, _i64, _p, _p, _p]),
     "cfk_flag_indices": (_int, [_p, _i64, _p, _p, _p]),
     # native NCRF ingestion (host pointers)
     "cfk_ncrf_last_error": (ctypes.c_char_p, []),

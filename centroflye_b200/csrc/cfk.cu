@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/cfk.h"
@@ -789,6 +790,155 @@ cloud_build_kernel(const uint32_t* __restrict__ packed, const int64_t* __restric
   if (threadIdx.x == 0) unit_cnt[u] = written;
 }
 
+// --------------------------------------------------------------------------------------------
+// Stage B, warp form (the default): one WARP per unit, no block barriers.
+//   * lane l rolls the contiguous run [l * S, (l + 1) * S) of the unit's k-mer starts (S = ceil(nk / 32)): one packed
+//     word per 16 bases instead of one load per base, and the first probes of CLW_BATCH consecutive k-mers are in
+//     flight together (every probe is an L2 round trip into the rare index);
+//   * hits are appended to a warp-private shared-memory list with ballot / popc (no atomics); a unit with more hits
+//     than the list holds is collected again straight into its global scratch run;
+//   * sort + unique are warp-synchronous (bitonic network over the list, __syncwarp between stages).
+// --------------------------------------------------------------------------------------------
+constexpr int CLW_WARPS = 8;      // warps (= units in flight) per block
+constexpr int CLW_LIST = 512;     // ids per warp-private list
+constexpr int CLW_BATCH = 4;      // k-mers whose first probe is issued together
+
+// ascending bitonic sort of data[0..n) by one warp (shared or global memory)
+__device__ void warp_sort_u32(uint32_t* data, int n) {
+  const int lane = threadIdx.x & 31;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int h = 1; h < np2; h <<= 1) {
+    for (int i = lane; i < np2 / 2; i += 32) {
+      const int blk = i / h, off = i % h;
+      const int lo = blk * 2 * h + off, hi = blk * 2 * h + 2 * h - 1 - off;
+      if (hi < n) {
+        const uint32_t a = data[lo], b = data[hi];
+        if (b < a) { data[lo] = b; data[hi] = a; }
+      }
+    }
+    __syncwarp();
+    for (int hh = h >> 1; hh >= 1; hh >>= 1) {
+      for (int i = lane; i < np2 / 2; i += 32) {
+        const int blk = i / hh, off = i % hh;
+        const int lo = blk * 2 * hh + off, hi = lo + hh;
+        if (hi < n) {
+          const uint32_t a = data[lo], b = data[hi];
+          if (b < a) { data[lo] = b; data[hi] = a; }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CLW_WARPS * 32)
+cloud_build_warp_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ unit_off,
+                        const int32_t* __restrict__ unit_len, const int64_t* __restrict__ unit_kbase, int64_t n_units, int k,
+                        const uint64_t* __restrict__ idx_keys, const uint32_t* __restrict__ idx_vals, int64_t cap,
+                        uint32_t* tmp_ids, int32_t* unit_cnt) {
+  __shared__ uint32_t s_list[CLW_WARPS][CLW_LIST];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int64_t u = (int64_t)blockIdx.x * CLW_WARPS + warp;
+  if (u >= n_units) return;
+  const int nk = unit_len[u] - k + 1;
+  if (nk <= 0) {
+    if (lane == 0) unit_cnt[u] = 0;
+    return;
+  }
+  uint32_t* out = tmp_ids + unit_kbase[u];  // nk slots
+  const int64_t off = unit_off[u];
+  const uint64_t mask = (1ull << (2 * k)) - 1;
+  const int S = (nk + 31) >> 5;
+  const int p_begin = min(lane * S, nk), p_end = min(p_begin + S, nk);
+  uint32_t* list = s_list[warp];
+  int list_cap = CLW_LIST;
+  int n = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    n = 0;
+    // the run's first k - 1 bases
+    int64_t pos = off + p_begin;  // absolute base index of the next base to shift in
+    uint32_t word = 0;
+    uint64_t kmer = 0;
+    if (p_begin < p_end) {
+      word = __ldg(packed + (pos >> 4));
+      for (int i = 0; i < k - 1; ++i, ++pos) {
+        if ((pos & 15) == 0) word = __ldg(packed + (pos >> 4));
+        kmer = (kmer << 2) | ((word >> ((pos & 15) << 1)) & 3u);
+      }
+    }
+    for (int p0 = p_begin; __any_sync(FULL, p0 < p_end); p0 += CLW_BATCH) {
+      uint64_t km[CLW_BATCH], key[CLW_BATCH];
+      int64_t slot[CLW_BATCH];
+#pragma unroll
+      for (int j = 0; j < CLW_BATCH; ++j) {
+        km[j] = EMPTY;  // never a k-mer (k <= 31)
+        key[j] = EMPTY;
+        slot[j] = 0;
+        if (p0 + j < p_end) {
+          if ((pos & 15) == 0) word = __ldg(packed + (pos >> 4));
+          kmer = ((kmer << 2) | ((word >> ((pos & 15) << 1)) & 3u)) & mask;
+          ++pos;
+          km[j] = kmer;
+          slot[j] = home_slot(mix64(kmer), cap);
+          key[j] = __ldg(idx_keys + slot[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CLW_BATCH; ++j) {
+        uint32_t id = 0;
+        bool hit = false;
+        if (km[j] != EMPTY) {
+          uint64_t cur = key[j];
+          int64_t sl = slot[j];
+          for (int64_t probes = 0; probes < cap; ++probes) {
+            if (cur == km[j]) { hit = true; break; }
+            if (cur == EMPTY) break;
+            if (++sl == cap) sl = 0;
+            cur = __ldg(idx_keys + sl);
+          }
+          if (hit) id = __ldg(idx_vals + sl);
+        }
+        const unsigned bal = __ballot_sync(FULL, hit);
+        if (hit) {
+          const int at = n + __popc(bal & lt);
+          if (at < list_cap) list[at] = id;
+        }
+        n += __popc(bal);
+      }
+    }
+    __syncwarp();
+    if (n <= list_cap) break;
+    list = out;  // more hits than the shared list holds: collect again into the unit's global run (nk slots)
+    list_cap = nk;
+  }
+  if (n == 0) {
+    if (lane == 0) unit_cnt[u] = 0;
+    return;
+  }
+  warp_sort_u32(list, n);
+  // unique: keep the first of every run; tiles of 32 (in place when list == out: a tile is read before it is written,
+  // and writes never pass the read position)
+  int written = 0;
+  uint32_t prev = 0;
+  for (int t0 = 0; t0 < n; t0 += 32) {
+    const int i = t0 + lane;
+    uint32_t v = 0;
+    if (i < n) v = list[i];
+    uint32_t before = __shfl_up_sync(FULL, v, 1);
+    if (lane == 0) before = prev;
+    const bool keep = i < n && (i == 0 || before != v);
+    const unsigned bal = __ballot_sync(FULL, keep);
+    prev = __shfl_sync(FULL, v, 31);
+    __syncwarp();
+    if (keep) out[written + __popc(bal & lt)] = v;
+    written += __popc(bal);
+    __syncwarp();
+  }
+  if (lane == 0) unit_cnt[u] = written;
+}
+
 // ---- exclusive scan int32 -> int64 (3 phases) ------------------------------------------------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
@@ -958,6 +1108,12 @@ __device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* __restrict__ 
 
 // usplit[7 u + j - 1] = position of the first id >= (n_kmers * j) >> 3 in unit u's sorted list, j = 1..7:
 // lets stage C cut any unit list at octant boundaries of the id space without searching.
+__global__ void occ_last_kernel(const uint32_t* __restrict__ occ, int64_t n, const uint32_t* __restrict__ unit_last,
+                                uint32_t* __restrict__ occ_last) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) occ_last[i] = __ldg(unit_last + occ[i]);
+}
+
 __global__ void unit_split_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids, int64_t n_units,
                                   int64_t n_kmers, uint32_t* usplit) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1350,20 +1506,27 @@ __device__ void pair_source(uint32_t tbase, const PairArgs& A, int dmin, int dli
   }
 }
 
+// index of the last unit of the read holding unit g = occurrence t of the source: from the per-occurrence copy
+// (occ_last, contiguous like occ itself) when the caller built one, else through unit_last[g] (a dependent random load)
+__device__ __forceinline__ int64_t last_unit_of(const uint32_t* __restrict__ unit_last, const uint32_t* __restrict__ last_a,
+                                                int64_t t, int64_t g) {
+  return (int64_t)(last_a ? __ldg(last_a + t) : __ldg(unit_last + g));
+}
+
 // Per-source prologue shared by both stage-C kernels.  Adds the reference's number of `+= 1` executions for
 // this source (dbkr.py:126) to incr_total, in closed form: every id of every unit g + d, d in [dmin, max_d],
 // minus the occurrences of a itself in them.  Returns the largest distance worth streaming (exact pruning:
 // cnt[d][a][b] >= min_cov needs >= min_cov occurrences whose read still has a unit g + d), dmin - 1 if none.
 __device__ int source_scope(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ unit_last,
                             const uint32_t* __restrict__ occ_a, int64_t m, int dmin, int max_d, uint32_t min_cov,
-                            int64_t& incr_total) {
+                            int64_t& incr_total, const uint32_t* __restrict__ last_a = nullptr) {
   const int lane = threadIdx.x & 31;
   int64_t entries = 0, self = 0, maxrem = 0;
   for (int64_t t0 = 0; t0 < m; t0 += 32) {
     const int64_t t = t0 + lane;
     if (t < m) {
       const int64_t g = (int64_t)__ldg(occ_a + t);
-      const int64_t last = (int64_t)__ldg(unit_last + g);
+      const int64_t last = last_unit_of(unit_last, last_a, t, g);
       const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, last);
       if (lo <= hi) {
         entries += __ldg(unit_ptr + hi + 1) - __ldg(unit_ptr + lo);
@@ -1391,7 +1554,7 @@ __device__ int source_scope(const int64_t* __restrict__ unit_ptr, const uint32_t
         bool ge = false;
         if (t < m) {
           const int64_t g = (int64_t)__ldg(occ_a + t);
-          ge = (int64_t)__ldg(unit_last + g) - g >= mid;
+          ge = last_unit_of(unit_last, last_a, t, g) - g >= mid;
         }
         c += __popc(__ballot_sync(FULL, ge));
       }
@@ -1538,6 +1701,7 @@ struct SketchArgs {
   const uint32_t* __restrict__ ids;
   const uint2* __restrict__ codes;
   const uint32_t* __restrict__ unit_last;
+  const uint32_t* __restrict__ last_a;  // unit_last[occ_a[t]] per occurrence, or nullptr
   const uint32_t* __restrict__ occ_a;
   int64_t m;
   int64_t n_kmers;
@@ -1599,7 +1763,7 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
       const int64_t t = (nd == 1) ? it : it / nd;
       const int64_t g = (int64_t)__ldg(A.occ_a + t);
       const int64_t u = g + d0 + (it - t * nd);
-      if (u <= (int64_t)__ldg(A.unit_last + g)) {
+      if (u <= last_unit_of(A.unit_last, A.last_a, t, g)) {
         const int64_t p0 = __ldg(A.unit_ptr + u);
         up = (uint32_t)p0;
         ue = (uint32_t)__ldg(A.unit_ptr + u + 1);
@@ -1712,7 +1876,7 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
         const int64_t t = t0 + lane;
         if (t < A.m) {
           const int64_t g = (int64_t)__ldg(A.occ_a + t);
-          const int64_t lim = (int64_t)__ldg(A.unit_last + g) + 1;
+          const int64_t lim = last_unit_of(A.unit_last, A.last_a, t, g) + 1;
           const int64_t u = g + d0 + jb;
           const uint32_t p0 = (uint32_t)__ldg(A.unit_ptr + min(u, lim)), p1 = (uint32_t)__ldg(A.unit_ptr + min(u + 1, lim)),
                          p2 = (uint32_t)__ldg(A.unit_ptr + min(u + 2, lim)), p3 = (uint32_t)__ldg(A.unit_ptr + min(u + 3, lim)),
@@ -1754,8 +1918,9 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
 __global__ void __launch_bounds__(SK_WARPS * 32, 1)
 pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids, const uint2* __restrict__ codes,
                    const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
-                   const uint32_t* __restrict__ occ, int64_t n_kmers, int64_t a_begin, int64_t a_end, int32_t a_stride,
-                   int32_t min_d, int32_t max_d, uint32_t min_cov, uint4* cand, int64_t max_cand, int64_t* counters) {
+                   const uint32_t* __restrict__ occ, const uint32_t* __restrict__ occ_last, int64_t n_kmers, int64_t a_begin,
+                   int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint4* cand,
+                   int64_t max_cand, int64_t* counters) {
   extern __shared__ __align__(16) unsigned char pc_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(pc_smem) + (uint32_t)warp * SK_WARP_BYTES;
@@ -1771,9 +1936,10 @@ pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restr
     const int64_t o0 = occ_ptr[a], m = occ_ptr[a + 1] - o0;
     if (m == 0) continue;
     const uint32_t* occ_a = occ + o0;
-    const int dlim = source_scope(unit_ptr, unit_last, occ_a, m, dmin, max_d, min_cov, incr_total);
+    const uint32_t* last_a = occ_last ? occ_last + o0 : nullptr;
+    const int dlim = source_scope(unit_ptr, unit_last, occ_a, m, dmin, max_d, min_cov, incr_total, last_a);
     if (dlim < dmin) continue;
-    SketchArgs A{unit_ptr, ids, codes, unit_last, occ_a, m, n_kmers, a, min_cov - 1u, cand, max_cand, counters};
+    SketchArgs A{unit_ptr, ids, codes, unit_last, last_a, occ_a, m, n_kmers, a, min_cov - 1u, cand, max_cand, counters};
     sketch_source(tbase, A, dmin, dlim, splits);
   }
   if (lane == 0) {
@@ -1789,24 +1955,25 @@ pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restr
 // (double)cnt / (double)all_occ >= rel_threshold (dbkr.py:136,145).
 // ============================================================================================
 __global__ void pair_join_kernel(const uint4* __restrict__ cand, int64_t n_cand, const int64_t* __restrict__ occ_ptr,
-                                 const uint32_t* __restrict__ occ, const uint32_t* __restrict__ unit_last,
-                                 int32_t min_d, int32_t max_d, uint32_t min_cov, double rel_threshold, uint4* edges,
-                                 int64_t max_edges, uint8_t* selected, int64_t* counters) {
+                                 const uint32_t* __restrict__ occ, const uint32_t* __restrict__ occ_last,
+                                 const uint32_t* __restrict__ unit_last, int32_t min_d, int32_t max_d, uint32_t min_cov,
+                                 double rel_threshold, uint4* edges, int64_t max_edges, uint8_t* selected, int64_t* counters) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t dmin = max(min_d, 1);
   uint4 c = make_uint4(0, 0, 0, 0);
   uint32_t dmask = 0;  // distances d0 + j of the chunk at which the pair co-occurs
   uint32_t cnt0 = 0;   // cnt[d0][a][b], gathered by the first join (most chunks are a single distance)
   uint64_t all_occ = 0;
-  const uint32_t *oa = occ, *oa_end = occ, *ob = occ, *ob_end = occ;
+  const uint32_t *oa = occ, *oa_end = occ, *ob = occ, *ob_end = occ, *la = nullptr;
   if (i < n_cand) {
     c = cand[i];
     oa = occ + occ_ptr[c.x]; oa_end = occ + occ_ptr[c.x + 1];
+    if (occ_last) la = occ_last + occ_ptr[c.x];
     ob = occ + occ_ptr[c.y]; ob_end = occ + occ_ptr[c.y + 1];
     const uint32_t* j = ob;
     for (const uint32_t* t = oa; t < oa_end; ++t) {
       const int64_t g = __ldg(t);
-      const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, (int64_t)__ldg(unit_last + g));
+      const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, last_unit_of(unit_last, la, t - oa, g));
       if (lo > hi) continue;
       while (j < ob_end && (int64_t)__ldg(j) < lo) ++j;
       for (const uint32_t* jj = j; jj < ob_end; ++jj) {
@@ -1833,7 +2000,7 @@ __global__ void pair_join_kernel(const uint4* __restrict__ cand, int64_t n_cand,
         const uint32_t* j = ob;
         for (const uint32_t* t = oa; t < oa_end; ++t) {  // cnt[d][a][b]: occurrences g of a with g + d holding b inside the read
           const int64_t g = __ldg(t);
-          if (g + d > (int64_t)__ldg(unit_last + g)) continue;
+          if (g + d > last_unit_of(unit_last, la, t - oa, g)) continue;
           while (j < ob_end && (int64_t)__ldg(j) < g + d) ++j;
           if (j < ob_end && (int64_t)__ldg(j) == g + d) ++cnt;
         }
@@ -2011,9 +2178,16 @@ int cfk_cloud_build(const uint32_t* packed, const int64_t* unit_off, const int32
   if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_cloud_build: k must be in [1, 31]");
   if (n_units < 0 || n_units >= (1ll << 31) || cap < 1) return fail(CFK_ERR_INVALID, "cfk_cloud_build: bad sizes");
   if (n_units == 0) return CFK_OK;
-  cloud_build_kernel<<<(unsigned)n_units, CL_THREADS, 0, (cudaStream_t)stream>>>(packed, unit_off, unit_len, unit_kbase, k,
-                                                                                 idx_keys, idx_vals, cap, tmp_ids, unit_cnt);
-  CFK_CHECK_LAUNCH("cloud_build_kernel", 1);
+  static const bool block_form = [] { const char* e = getenv("CFK_CLOUD_MODE"); return e && !strcmp(e, "block"); }();
+  if (block_form) {  // the first version of the kernel, one block per unit (A/B and cross-checks)
+    cloud_build_kernel<<<(unsigned)n_units, CL_THREADS, 0, (cudaStream_t)stream>>>(packed, unit_off, unit_len, unit_kbase, k,
+                                                                                   idx_keys, idx_vals, cap, tmp_ids, unit_cnt);
+    CFK_CHECK_LAUNCH("cloud_build_kernel", 1);
+    return CFK_OK;
+  }
+  cloud_build_warp_kernel<<<(unsigned)blocks_for(n_units, CLW_WARPS), CLW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+      packed, unit_off, unit_len, unit_kbase, n_units, k, idx_keys, idx_vals, cap, tmp_ids, unit_cnt);
+  CFK_CHECK_LAUNCH("cloud_build_warp_kernel", 1);
   return CFK_OK;
 }
 
@@ -2094,6 +2268,14 @@ int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_str
   return CFK_OK;
 }
 
+int cfk_occ_last(const uint32_t* occ, int64_t n, const uint32_t* unit_last, uint32_t* occ_last, cfk_stream_t stream) {
+  if (n < 0) return fail(CFK_ERR_INVALID, "cfk_occ_last: n < 0");
+  if (n == 0) return CFK_OK;
+  occ_last_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(occ, n, unit_last, occ_last);
+  CFK_CHECK_LAUNCH("occ_last_kernel", 1);
+  return CFK_OK;
+}
+
 int cfk_unit_splits(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, int64_t n_entries, int64_t n_kmers,
                     uint32_t* usplit, cfk_stream_t stream) {
   if (n_units < 0 || n_kmers < 0 || n_entries < 0 || n_entries >= (1ll << 32))
@@ -2149,7 +2331,7 @@ int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_uni
 }
 
 int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* unit_last,
-                    const int64_t* occ_ptr, const uint32_t* occ, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
+                    const int64_t* occ_ptr, const uint32_t* occ, const uint32_t* occ_last, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
                     int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint32_t* cand,
                     int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream) {
   if (n_entries < 0 || n_entries >= (1ll << 32))
@@ -2170,19 +2352,19 @@ int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t
     attr_done = true;
   }
   pair_sketch_kernel<<<(unsigned)n_blocks, SK_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      unit_ptr, ids, (const uint2*)codes, unit_last, occ_ptr, occ, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
+      unit_ptr, ids, (const uint2*)codes, unit_last, occ_ptr, occ, occ_last, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
       max_cand, counters);
   CFK_CHECK_LAUNCH("pair_sketch_kernel", 1);
   return CFK_OK;
 }
 
-int cfk_pair_join(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ,
+int cfk_pair_join(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ, const uint32_t* occ_last,
                   const uint32_t* unit_last, int32_t min_d, int32_t max_d, uint32_t min_cov, double rel_threshold,
                   uint32_t* edges, int64_t max_edges, uint8_t* selected, int64_t* counters, cfk_stream_t stream) {
   if (n_cand < 0 || max_edges < 0) return fail(CFK_ERR_INVALID, "cfk_pair_join: bad sizes");
   if (n_cand == 0) return CFK_OK;
   pair_join_kernel<<<(unsigned)blocks_for(n_cand, 128), 128, 0, (cudaStream_t)stream>>>(
-      (const uint4*)cand, n_cand, occ_ptr, occ, unit_last, min_d, max_d, min_cov, rel_threshold, (uint4*)edges,
+      (const uint4*)cand, n_cand, occ_ptr, occ, occ_last, unit_last, min_d, max_d, min_cov, rel_threshold, (uint4*)edges,
       max_edges, selected, counters);
   CFK_CHECK_LAUNCH("pair_join_kernel", 1);
   return CFK_OK;

@@ -159,7 +159,7 @@ class DistCounts(Mapping):
     def occurrences(self):
         if self._occ is None:
             st = self.state
-            self._occ = st.engine.build_occurrences(st.csr, st.index.n, self.unit_lo, self.unit_hi)
+            self._occ = st.engine.build_occurrences(st.csr, st.index.n, self.unit_lo, self.unit_hi, st.unit_last)
         return self._occ
 
     def run(self, min_coverage, rel_threshold):

@@ -99,6 +99,8 @@ class Engine:
         self.cand_hint = 1 << 20
         self.edge_hint = 1 << 20
         self.select_hint = {}  # (lo > 0, with_counts) -> output capacity that held last time
+        self.use_occ_last = 1     # stage C/D read unit_last through a per-occurrence copy (0: chase unit_last[g])
+        self.index_cap_mult = 0   # slots per key of the rare-set probe table; 0 = by size (build_index)
         self.table_load = 0.6  # distinct k-mers <= occurrences, so the stage-A table is at most this full
         # stage C kernel: "auto" = sketch where it applies, "exact" = always the exact tables, "sketch" = insist
         self.pair_mode = os.environ.get("CFK_PAIR_MODE", "auto")
@@ -305,7 +307,10 @@ class Engine:
         t = self.torch
         n = int(keys.numel())
         sorted_keys = keys.contiguous() if presorted else self.sort_keys(keys.clone())
-        cap = max(64, 2 * n + 1)
+        # slots per key: stage B probes this table once per k-mer and is bound by L2 sector throughput, so every probe
+        # saved counts; 8x keeps chains near 1 probe while the table (12 B per slot) still sits in the 126 MB L2
+        mult = self.index_cap_mult or (8 if n <= (1 << 20) else 4 if n <= (1 << 22) else 2)
+        cap = max(64, mult * n + 1)
         idx_keys = t.full((cap,), -1, dtype=t.int64, device=self.device)
         idx_vals = self._zeros(cap, t.int32)
         counters = self._counters()
@@ -374,7 +379,9 @@ class Engine:
         return CloudCSR(unit_ptr=new_ptr, ids=new_ids[:E], n_units=U, n_entries=E)
 
     # ---- stage C / D ------------------------------------------------------------------------
-    def build_occurrences(self, csr, n_kmers, unit_lo=0, unit_hi=None):
+    def build_occurrences(self, csr, n_kmers, unit_lo=0, unit_hi=None, unit_last=None):
+        """-> (occ_ptr, occ, occ_last): the inverted cloud CSR; occ_last (unit_last gathered per occurrence) is None
+        when unit_last is not given."""
         t = self.torch
         unit_hi = csr.n_units if unit_hi is None else unit_hi
         mult = self.id_histogram(csr, n_kmers, unit_lo, unit_hi)
@@ -385,7 +392,11 @@ class Engine:
         _lib.call("cfk_occ_fill", self._p(csr.unit_ptr), self._p(csr.ids), unit_lo, unit_hi, self._p(occ_ptr),
                   self._p(cursor), self._p(occ), self._stream())
         _lib.call("cfk_occ_sort", self._p(occ_ptr), self._p(occ), n_kmers, self._stream())
-        return occ_ptr, occ
+        occ_last = None
+        if unit_last is not None and self.use_occ_last:
+            occ_last = self._empty(n_occ, t.int32)
+            _lib.call("cfk_occ_last", self._p(occ), n_occ, self._p(unit_last), self._p(occ_last), self._stream())
+        return occ_ptr, occ, occ_last
 
     def dist_edges(self, csr, unit_last, n_kmers, min_d, max_d, min_cov, rel_threshold=0.8,
                    unit_lo=0, unit_hi=None, a_begin=0, a_end=None, a_stride=1, occurrences=None):
@@ -398,7 +409,8 @@ class Engine:
                            selected=self._empty(0, t.int32)[:0], n_candidates=0, n_increments=0, n_splits=0)
         if n_kmers == 0 or csr.n_entries == 0 or max_d < max(min_d, 1):
             return empty
-        occ_ptr, occ = occurrences if occurrences is not None else self.build_occurrences(csr, n_kmers, unit_lo, unit_hi)
+        occ_ptr, occ, occ_last = (occurrences if occurrences is not None
+                                  else self.build_occurrences(csr, n_kmers, unit_lo, unit_hi, unit_last))
         min_cov_u = int(min(max(min_cov, 0), U32_MAX))
         # stage C flavour: the sketch kernel serves min_cov in [3, 255]; the exact tables serve anything
         use_sketch = self.pair_mode != "exact" and SKETCH_MIN_COV <= min_cov_u <= SKETCH_MAX_COV
@@ -420,9 +432,9 @@ class Engine:
             with self._stage("pair_candidates"):
                 if use_sketch:
                     _lib.call("cfk_pair_sketch", self._p(csr.unit_ptr), self._p(csr.ids), self._p(codes),
-                              self._p(unit_last), self._p(occ_ptr), self._p(occ), csr.n_entries, n_kmers, a_begin, a_end,
-                              a_stride, int(min_d), int(max_d), min_cov_u, self._p(cand), max_cand, self._p(counters),
-                              self.n_sms, self._stream())
+                              self._p(unit_last), self._p(occ_ptr), self._p(occ), self._p(occ_last), csr.n_entries, n_kmers,
+                              a_begin, a_end, a_stride, int(min_d), int(max_d), min_cov_u, self._p(cand), max_cand,
+                              self._p(counters), self.n_sms, self._stream())
                 else:
                     _lib.call("cfk_pair_candidates", self._p(csr.unit_ptr), self._p(csr.ids), self._p(unit_last),
                               self._p(occ_ptr), self._p(occ), self._p(usplit), csr.n_entries, n_kmers, a_begin, a_end,
@@ -443,7 +455,8 @@ class Engine:
             edges = self._empty(max_edges * 4, t.int32)
             counters2 = self._counters()
             with self._stage("pair_join"):
-                _lib.call("cfk_pair_join", self._p(cand), n_cand, self._p(occ_ptr), self._p(occ), self._p(unit_last),
+                _lib.call("cfk_pair_join", self._p(cand), n_cand, self._p(occ_ptr), self._p(occ), self._p(occ_last),
+                          self._p(unit_last),
                           int(min_d), int(max_d), min_cov_u, float(rel_threshold), self._p(edges), max_edges,
                           self._p(selected), self._p(counters2), self._stream())
             c2 = counters2.cpu()

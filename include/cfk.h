@@ -171,6 +171,9 @@ int cfk_cloud_filter_write(const int64_t* unit_ptr, const uint32_t* ids, int64_t
 int cfk_occ_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, int64_t unit_hi,
                  const int64_t* occ_ptr, int32_t* cursor, uint32_t* occ, cfk_stream_t stream);
 int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_stream_t stream);
+/* occ_last[i] = unit_last[occ[i]]: the last unit of the read of every occurrence, laid out like occ
+ * itself, so that cfk_pair_sketch / cfk_pair_join stream it instead of chasing unit_last[g]. */
+int cfk_occ_last(const uint32_t* occ, int64_t n, const uint32_t* unit_last, uint32_t* occ_last, cfk_stream_t stream);
 
 /* usplit[7 u + j - 1] (j = 1..7) = position in ids[] of the first id of unit u that is
  * >= (n_kmers * j) >> 3: the per-unit octant split table cfk_pair_candidates uses to cut a unit
@@ -209,13 +212,15 @@ int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint
  * (8-byte aligned) private to these two functions: per cloud entry the hash of its id (low
  * CFK_SKETCH_BITS bits) and, in bit 15, whether another id of the same unit with the same hash
  * precedes it, stored in 128-entry blocks per unit so that a lane fetches the four entries it
- * serves in a step with one 8-byte load (the tail of a unit's last block is padding). */
+ * serves in a step with one 8-byte load (the tail of a unit's last block is padding).
+ * (cfk_pair_sketch's occ_last: see below.) */
 int cfk_sketch_bits(void);
 int cfk_sketch_warps_per_block(void);
 int64_t cfk_sketch_codes_elems(int64_t n_entries, int64_t n_units);
 int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, cfk_stream_t stream);
+/* occ_last = cfk_occ_last output, or NULL (unit_last[g] is looked up instead). */
 int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* unit_last,
-                    const int64_t* occ_ptr, const uint32_t* occ, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
+                    const int64_t* occ_ptr, const uint32_t* occ, const uint32_t* occ_last, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
                     int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov,
                     uint32_t* cand, int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
 
@@ -226,8 +231,9 @@ int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t
  * (IEEE double division, the operation Python performs at :145), appends it to edges and flags
  * both endpoints in selected[] (uint8, zeroed by the caller).
  * counters (zeroed): [0] edges found (also beyond max_edges; nothing is written past
- * max_edges), [2] number of (a, b, d) with cnt >= min_cov (the reference's candidate dict). */
-int cfk_pair_join(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ,
+ * max_edges), [2] number of (a, b, d) with cnt >= min_cov (the reference's candidate dict).
+ * occ_last = cfk_occ_last output, or NULL. */
+int cfk_pair_join(const uint32_t* cand, int64_t n_cand, const int64_t* occ_ptr, const uint32_t* occ, const uint32_t* occ_last,
                   const uint32_t* unit_last, int32_t min_d, int32_t max_d, uint32_t min_cov, double rel_threshold,
                   uint32_t* edges, int64_t max_edges, uint8_t* selected, int64_t* counters, cfk_stream_t stream);
 
