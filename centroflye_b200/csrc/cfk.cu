@@ -1604,6 +1604,100 @@ pair_candidates_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __r
   }
 }
 
+// ---- stage D core (pair_join_kernel, one thread per candidate).  All 32 lanes of a warp call it; `active` lanes hold a
+// candidate (a, b, d0, d1).  (Running it inside the sketch kernel -- one lane per parked candidate of the warp's source,
+// no candidate array -- was measured and dropped: 22.0 ms against 16.7 + 2.8 ms, the sketch kernel paid 16 more
+// registers per thread.)
+// Joins the sorted occurrence lists of a and b: all_occ = #{(g, g') : g' - g in [dmin, dmax], same read}
+// (dbkr.py:143) and the exact cnt[d][a][b] for the distances of the chunk; keeps (a, b, d, cnt) iff cnt >= min_cov and
+// (double)cnt / (double)all_occ >= rel_threshold (dbkr.py:136,145).  Returns the lane's number of (d) with cnt >= min_cov.
+struct JoinArgs {
+  const int64_t* __restrict__ occ_ptr;
+  const uint32_t* __restrict__ occ;
+  const uint32_t* __restrict__ occ_last;   // may be nullptr
+  const uint32_t* __restrict__ unit_last;
+  uint32_t dmin, dmax, min_cov;
+  double rel_threshold;
+  uint4* edges;
+  int64_t max_edges;
+  uint8_t* selected;
+  int64_t* edge_counter;
+};
+
+__device__ __forceinline__ uint32_t join_candidate(bool active, uint4 c, const JoinArgs& J) {
+  // 32-bit cursors into occ[] (its length is the number of cloud entries, < 2^32) and unit distances relative to g,
+  // the current unit of b kept in a register (0xFFFFFFFF behind the end of the list: no unit has that index)
+  constexpr uint32_t END = 0xFFFFFFFFu;
+  uint32_t dmask = 0;  // distances d0 + j of the chunk at which the pair co-occurs
+  uint32_t cnt0 = 0;   // cnt[d0][a][b], gathered by the first join (most chunks are a single distance)
+  uint64_t all_occ = 0;
+  uint32_t ia = 0, ia_end = 0, ib0 = 0, ib_end = 0;
+  if (active) {
+    ia = (uint32_t)J.occ_ptr[c.x]; ia_end = (uint32_t)J.occ_ptr[c.x + 1];
+    ib0 = (uint32_t)J.occ_ptr[c.y]; ib_end = (uint32_t)J.occ_ptr[c.y + 1];
+    const uint32_t width = c.w - c.z;
+    uint32_t ib = ib0;
+    uint32_t bj = ib < ib_end ? __ldg(J.occ + ib) : END;
+    for (uint32_t t = ia; t < ia_end; ++t) {
+      const uint32_t g = __ldg(J.occ + t);
+      const uint32_t rem = (J.occ_last ? __ldg(J.occ_last + t) : __ldg(J.unit_last + g)) - g;  // units behind g in its read
+      if (J.dmin > rem) continue;
+      const uint32_t lo = g + J.dmin, hi = g + min(J.dmax, rem);  // <= last unit of the read: no wrap
+      while (bj < lo) {
+        ++ib;
+        bj = ib < ib_end ? __ldg(J.occ + ib) : END;
+      }
+      uint32_t jj = ib, v = bj;
+      while (v <= hi) {  // END > hi always
+        ++all_occ;
+        const uint32_t dj = (v - g) - c.z;  // wraps to a huge value below d0
+        if (dj <= width) dmask |= 1u << dj;
+        cnt0 += dj == 0u;
+        ++jj;
+        v = jj < ib_end ? __ldg(J.occ + jj) : END;
+      }
+    }
+  }
+  uint32_t n_cand_d = 0;
+  while (__any_sync(FULL, dmask != 0)) {
+    bool keep = false;
+    uint32_t d = 0, cnt = 0;
+    if (dmask) {
+      const uint32_t dj = (uint32_t)(__ffs(dmask) - 1);
+      d = c.z + dj;
+      dmask &= dmask - 1;
+      if (dj == 0u) {
+        cnt = cnt0;
+      } else {
+        uint32_t ib = ib0;
+        uint32_t bj = ib < ib_end ? __ldg(J.occ + ib) : END;
+        for (uint32_t t = ia; t < ia_end; ++t) {  // cnt[d][a][b]: occurrences g of a with g + d holding b inside the read
+          const uint32_t g = __ldg(J.occ + t);
+          const uint32_t rem = (J.occ_last ? __ldg(J.occ_last + t) : __ldg(J.unit_last + g)) - g;
+          if (d > rem) continue;
+          const uint32_t want = g + d;
+          while (bj < want) {
+            ++ib;
+            bj = ib < ib_end ? __ldg(J.occ + ib) : END;
+          }
+          cnt += bj == want;
+        }
+      }
+      if (cnt >= J.min_cov) {
+        ++n_cand_d;
+        keep = ((double)cnt / (double)all_occ) >= J.rel_threshold;
+      }
+    }
+    const int64_t pos = warp_append(keep, J.edge_counter);
+    if (keep) {
+      if (pos < J.max_edges) J.edges[pos] = make_uint4(c.x, c.y, d, cnt);
+      J.selected[c.x] = 1;
+      J.selected[c.y] = 1;
+    }
+  }
+  return n_cand_d;
+}
+
 // ============================================================================================
 // Stage C, sketch form (the default for 3 <= min_cov <= 255).
 //
@@ -1959,64 +2053,11 @@ __global__ void pair_join_kernel(const uint4* __restrict__ cand, int64_t n_cand,
                                  const uint32_t* __restrict__ unit_last, int32_t min_d, int32_t max_d, uint32_t min_cov,
                                  double rel_threshold, uint4* edges, int64_t max_edges, uint8_t* selected, int64_t* counters) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t dmin = max(min_d, 1);
+  const JoinArgs J{occ_ptr, occ, occ_last, unit_last, (uint32_t)max(min_d, 1), (uint32_t)max(max_d, 0), min_cov, rel_threshold,
+                   edges, max_edges, selected, counters};
   uint4 c = make_uint4(0, 0, 0, 0);
-  uint32_t dmask = 0;  // distances d0 + j of the chunk at which the pair co-occurs
-  uint32_t cnt0 = 0;   // cnt[d0][a][b], gathered by the first join (most chunks are a single distance)
-  uint64_t all_occ = 0;
-  const uint32_t *oa = occ, *oa_end = occ, *ob = occ, *ob_end = occ, *la = nullptr;
-  if (i < n_cand) {
-    c = cand[i];
-    oa = occ + occ_ptr[c.x]; oa_end = occ + occ_ptr[c.x + 1];
-    if (occ_last) la = occ_last + occ_ptr[c.x];
-    ob = occ + occ_ptr[c.y]; ob_end = occ + occ_ptr[c.y + 1];
-    const uint32_t* j = ob;
-    for (const uint32_t* t = oa; t < oa_end; ++t) {
-      const int64_t g = __ldg(t);
-      const int64_t lo = g + dmin, hi = min(g + (int64_t)max_d, last_unit_of(unit_last, la, t - oa, g));
-      if (lo > hi) continue;
-      while (j < ob_end && (int64_t)__ldg(j) < lo) ++j;
-      for (const uint32_t* jj = j; jj < ob_end; ++jj) {
-        const int64_t u = __ldg(jj);
-        if (u > hi) break;
-        ++all_occ;
-        const uint32_t dj = (uint32_t)(u - g) - c.z;  // wraps to a huge value below d0
-        if (dj <= c.w - c.z) dmask |= 1u << dj;
-        cnt0 += dj == 0u;
-      }
-    }
-  }
-  uint32_t n_cand_d = 0;
-  while (__any_sync(FULL, dmask != 0)) {
-    bool keep = false;
-    uint32_t d = 0, cnt = 0;
-    if (dmask) {
-      const uint32_t dj = (uint32_t)(__ffs(dmask) - 1);
-      d = c.z + dj;
-      dmask &= dmask - 1;
-      if (dj == 0u) {
-        cnt = cnt0;
-      } else {
-        const uint32_t* j = ob;
-        for (const uint32_t* t = oa; t < oa_end; ++t) {  // cnt[d][a][b]: occurrences g of a with g + d holding b inside the read
-          const int64_t g = __ldg(t);
-          if (g + d > last_unit_of(unit_last, la, t - oa, g)) continue;
-          while (j < ob_end && (int64_t)__ldg(j) < g + d) ++j;
-          if (j < ob_end && (int64_t)__ldg(j) == g + d) ++cnt;
-        }
-      }
-      if (cnt >= min_cov) {
-        ++n_cand_d;
-        keep = ((double)cnt / (double)all_occ) >= rel_threshold;
-      }
-    }
-    const int64_t pos = warp_append(keep, counters);
-    if (keep) {
-      if (pos < max_edges) edges[pos] = make_uint4(c.x, c.y, d, cnt);
-      selected[c.x] = 1;
-      selected[c.y] = 1;
-    }
-  }
+  if (i < n_cand) c = cand[i];
+  uint32_t n_cand_d = join_candidate(i < n_cand, c, J);
   for (int o = 16; o >= 1; o >>= 1) n_cand_d += __shfl_xor_sync(FULL, n_cand_d, o);
   if ((threadIdx.x & 31) == 0 && n_cand_d) atomicAdd((unsigned long long*)(counters + 2), (unsigned long long)n_cand_d);
 }
