@@ -47,8 +47,8 @@ SIGNATURES = {
     "cfk_sketch_bits": (_int, []),
     "cfk_sketch_warps_per_block": (_int, []),
     "cfk_sketch_codes_elems": (_i64, [_i64, _i64]),
-    "cfk_sketch_codes": (_int, [_p, _p, _i64, _p, _p]),
-    "cfk_pair_sketch": (_int, [_p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p,
+    "cfk_sketch_codes": (_int, [_p, _p, _i64, _p, _p, _p]),
+    "cfk_pair_sketch": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p,
                                _i32, _p]),
     "cfk_pair_join": (_int, [_p, _i64, _p, _p, _p, _p, _i32, _i32, _u32, _f64, _p, _i64, _p, _p, _p]),
     "cfk_flag_indices": (_int, [_p, _i64, _p, _p, _p]),

@@ -1727,7 +1727,7 @@ constexpr int SK_TBL_BYTES = 1 << SK_BITS;
 constexpr uint32_t SK_OFF_MASK = 0x3FFFu;          // code bits 0..13: byte offset in the warp's table (hash, or the null byte)
 constexpr uint32_t SK_DUP = 0x8000u;               // code bit 15: do not store (duplicate hash inside the unit, or null)
 constexpr uint32_t SK_NULL = SK_DUP | (uint32_t)SK_TBL_BYTES;  // padding entry: reads the always-zero byte behind the table
-constexpr int SK_PAD_BYTES = 16;                   // that byte (and alignment of what follows)
+constexpr int SK_PAD_BYTES = 128;                  // always-zero words behind the table, one per bank: null entries of lane l read word l
 constexpr int SK_L2_SLOTS = 256;   // level-2 set, u32 slots holding b + 1
 constexpr int SK_L2_MAX = 192;
 constexpr int SK_Q_SLOTS = 256;    // queue of hot positions
@@ -1790,9 +1790,93 @@ __global__ void __launch_bounds__(256) sketch_codes_kernel(const int64_t* __rest
   }
 }
 
+// Bank-aware form of sketch_codes_kernel.  The byte counters of a pass are hit at random, so a row of 32 entries
+// costs ~2 shared-memory wavefronts for the load and again for the store (bank conflicts).  Here the entries of a
+// 128-entry window are PLACED: the r-th entry of the window whose counter lies in bank B goes to row r, lane B, so the
+// rows hold at most one entry per bank -- conflict-free -- as long as a bank has no more entries than the window has
+// rows; the overflow (about one entry in seven) fills the free slots, highest rows first, so that the conflicts
+// concentrate in the last row.  Free slots of lane l hold a null code that reads the always-zero pad word of bank l.
+// Because the order inside a window changes, the ids travel with the codes: perm_ids[block * 128 + 4 * lane + row]
+// is the id behind the code at that slot (the hot-id lookup of pair_sketch_kernel reads it instead of ids[]).
+__global__ void __launch_bounds__(256) sketch_codes_banked_kernel(const int64_t* __restrict__ unit_ptr,
+                                                                  const uint32_t* __restrict__ ids, int64_t n_units,
+                                                                  uint2* __restrict__ codes, uint4* __restrict__ perm_ids) {
+  __shared__ uint32_t bm[8][SK_TBL_BYTES / 32];
+  __shared__ int s_cnt[8][32];
+  __shared__ int s_nover[8];
+  __shared__ uint16_t s_code[8][SK_WINDOW], s_ocode[8][SK_WINDOW];
+  __shared__ uint32_t s_id[8][SK_WINDOW], s_oid[8][SK_WINDOW];
+  __shared__ uint8_t s_free[8][SK_WINDOW];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int64_t u = (int64_t)blockIdx.x * 8 + warp;
+  if (u >= n_units) return;
+  const int64_t b = unit_ptr[u], e = unit_ptr[u + 1];
+  if (b == e) return;
+  for (int i = lane; i < SK_TBL_BYTES / 32; i += 32) bm[warp][i] = 0;
+  __syncwarp();
+  int64_t blk = sk_block(b, u);
+  for (int64_t p0 = b; p0 < e; p0 += SK_WINDOW, ++blk) {
+    const int n = (int)min((int64_t)SK_WINDOW, e - p0), rows = (n + 31) >> 5;
+    s_cnt[warp][lane] = 0;
+    if (lane == 0) s_nover[warp] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // slot 4 * l + j of lane l: null until an entry is placed there
+      s_code[warp][4 * lane + j] = (uint16_t)(SK_DUP | (uint32_t)(SK_TBL_BYTES + 4 * lane));
+      s_id[warp][4 * lane + j] = 0u;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = 32 * j + lane;
+      if (q < n) {
+        const uint32_t id = ids[p0 + q];
+        const uint32_t h = sk_hash(id);
+        const uint32_t old = atomicOr(&bm[warp][h >> 5], 1u << (h & 31u));
+        const uint16_t code = (uint16_t)(h | (((old >> (h & 31u)) & 1u) ? SK_DUP : 0u));
+        const int bank = (int)((h >> 2) & 31u);
+        const int r = atomicAdd(&s_cnt[warp][bank], 1);
+        if (r < rows) {
+          s_code[warp][4 * bank + r] = code;
+          s_id[warp][4 * bank + r] = id;
+        } else {
+          const int o = atomicAdd(&s_nover[warp], 1);
+          s_ocode[warp][o] = code;
+          s_oid[warp][o] = id;
+        }
+      }
+    }
+    __syncwarp();
+    // free slots of the rows in use, highest row first
+    const int mine = min(s_cnt[warp][lane], rows);
+    int base = 0;
+    for (int r = rows - 1; r >= 0; --r) {
+      const bool fr = mine <= r;
+      const unsigned bal = __ballot_sync(FULL, fr);
+      if (fr) s_free[warp][base + __popc(bal & lt)] = (uint8_t)(4 * lane + r);
+      base += __popc(bal);
+    }
+    __syncwarp();
+    const int nover = s_nover[warp];  // <= base: the rows in use hold 32 * rows >= n slots
+    for (int o = lane; o < nover; o += 32) {
+      const int slot = s_free[warp][o];
+      s_code[warp][slot] = s_ocode[warp][o];
+      s_id[warp][slot] = s_oid[warp][o];
+    }
+    __syncwarp();
+    const uint32_t c0 = s_code[warp][4 * lane], c1 = s_code[warp][4 * lane + 1], c2 = s_code[warp][4 * lane + 2],
+                   c3 = s_code[warp][4 * lane + 3];
+    codes[blk * 32 + lane] = make_uint2(c0 | (c1 << 16), c2 | (c3 << 16));
+    perm_ids[blk * 32 + lane] = make_uint4(s_id[warp][4 * lane], s_id[warp][4 * lane + 1], s_id[warp][4 * lane + 2],
+                                           s_id[warp][4 * lane + 3]);
+    __syncwarp();
+  }
+}
+
 struct SketchArgs {
   const int64_t* __restrict__ unit_ptr;
-  const uint32_t* __restrict__ ids;
+  const uint32_t* __restrict__ ids;      // hot-id lookup: ids[] positions, or (banked codes) perm_ids[] slots
+  bool banked;
   const uint2* __restrict__ codes;
   const uint32_t* __restrict__ unit_last;
   const uint32_t* __restrict__ last_a;  // unit_last[occ_a[t]] per occurrence, or nullptr
@@ -1921,7 +2005,7 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const unsigned bal = __ballot_sync(FULL, hs[i]);
-          if (hs[i]) sts(qbase + (uint32_t)(qn + __popc(bal & lt)) * 4u, p + (uint32_t)lane + 32u * i);
+          if (hs[i]) sts(qbase + (uint32_t)(qn + __popc(bal & lt)) * 4u, A.banked ? (cb << 7) + 4u * (uint32_t)lane + (uint32_t)i : p + (uint32_t)lane + 32u * i);
           qn += __popc(bal);
         }
         if (qn > SK_Q_SLOTS - SK_WINDOW) {
@@ -2011,7 +2095,7 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
 
 __global__ void __launch_bounds__(SK_WARPS * 32, 1)
 pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids, const uint2* __restrict__ codes,
-                   const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
+                   const uint32_t* __restrict__ perm_ids, const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
                    const uint32_t* __restrict__ occ, const uint32_t* __restrict__ occ_last, int64_t n_kmers, int64_t a_begin,
                    int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint4* cand,
                    int64_t max_cand, int64_t* counters) {
@@ -2033,7 +2117,8 @@ pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restr
     const uint32_t* last_a = occ_last ? occ_last + o0 : nullptr;
     const int dlim = source_scope(unit_ptr, unit_last, occ_a, m, dmin, max_d, min_cov, incr_total, last_a);
     if (dlim < dmin) continue;
-    SketchArgs A{unit_ptr, ids, codes, unit_last, last_a, occ_a, m, n_kmers, a, min_cov - 1u, cand, max_cand, counters};
+    SketchArgs A{unit_ptr, perm_ids ? perm_ids : ids, perm_ids != nullptr, codes, unit_last, last_a, occ_a, m, n_kmers, a, min_cov - 1u, cand,
+                 max_cand, counters};
     sketch_source(tbase, A, dmin, dlim, splits);
   }
   if (lane == 0) {
@@ -2362,16 +2447,25 @@ int64_t cfk_sketch_codes_elems(int64_t n_entries, int64_t n_units) {
   return (sk_block(n_entries, n_units) + 1) * SK_WINDOW;
 }
 
-int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, cfk_stream_t stream) {
+int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, uint32_t* perm_ids,
+                     cfk_stream_t stream) {
   if (n_units < 0) return fail(CFK_ERR_INVALID, "cfk_sketch_codes: n_units < 0");
   if (n_units == 0) return CFK_OK;
   if (((uintptr_t)codes & 7u) != 0) return fail(CFK_ERR_INVALID, "cfk_sketch_codes: codes must be 8-byte aligned");
+  if (perm_ids != nullptr) {
+    if (((uintptr_t)perm_ids & 15u) != 0) return fail(CFK_ERR_INVALID, "cfk_sketch_codes: perm_ids must be 16-byte aligned");
+    sketch_codes_banked_kernel<<<(unsigned)blocks_for(n_units, 8), 256, 0, (cudaStream_t)stream>>>(unit_ptr, ids, n_units,
+                                                                                                   (uint2*)codes, (uint4*)perm_ids);
+    CFK_CHECK_LAUNCH("sketch_codes_banked_kernel", 1);
+    return CFK_OK;
+  }
   sketch_codes_kernel<<<(unsigned)blocks_for(n_units, 8), 256, 0, (cudaStream_t)stream>>>(unit_ptr, ids, n_units, (uint2*)codes);
   CFK_CHECK_LAUNCH("sketch_codes_kernel", 1);
   return CFK_OK;
 }
 
-int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* unit_last,
+int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* perm_ids,
+                    const uint32_t* unit_last,
                     const int64_t* occ_ptr, const uint32_t* occ, const uint32_t* occ_last, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
                     int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint32_t* cand,
                     int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream) {
@@ -2393,7 +2487,7 @@ int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t
     attr_done = true;
   }
   pair_sketch_kernel<<<(unsigned)n_blocks, SK_WARPS * 32, smem, (cudaStream_t)stream>>>(
-      unit_ptr, ids, (const uint2*)codes, unit_last, occ_ptr, occ, occ_last, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
+      unit_ptr, ids, (const uint2*)codes, perm_ids, unit_last, occ_ptr, occ, occ_last, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
       max_cand, counters);
   CFK_CHECK_LAUNCH("pair_sketch_kernel", 1);
   return CFK_OK;

@@ -99,6 +99,7 @@ class Engine:
         self.cand_hint = 1 << 20
         self.edge_hint = 1 << 20
         self.select_hint = {}  # (lo > 0, with_counts) -> output capacity that held last time
+        self.sketch_banked = 1    # stage C sketch: bank-aware placement of the codes (0: the ids' own order)
         self.use_occ_last = 1     # stage C/D read unit_last through a per-occurrence copy (0: chase unit_last[g])
         self.index_cap_mult = 0   # slots per key of the rare-set probe table; 0 = by size (build_index)
         self.table_load = 0.6  # distinct k-mers <= occurrences, so the stage-A table is at most this full
@@ -417,10 +418,12 @@ class Engine:
         if self.pair_mode == "sketch" and not use_sketch:
             raise CfkError(f"pair_mode=sketch needs {SKETCH_MIN_COV} <= min_coverage <= {SKETCH_MAX_COV}")
         if use_sketch:
-            codes = self._empty(int(self.lib.cfk_sketch_codes_elems(csr.n_entries, csr.n_units)), t.int16)
+            n_codes = int(self.lib.cfk_sketch_codes_elems(csr.n_entries, csr.n_units))
+            codes = self._empty(n_codes, t.int16)
+            perm = self._empty(n_codes, t.int32) if self.sketch_banked and n_codes < (1 << 32) else None
             with self._stage("sketch_codes"):
                 _lib.call("cfk_sketch_codes", self._p(csr.unit_ptr), self._p(csr.ids), csr.n_units, self._p(codes),
-                          self._stream())
+                          self._p(perm), self._stream())
         else:
             usplit = self._empty(7 * csr.n_units, t.int32)
             _lib.call("cfk_unit_splits", self._p(csr.unit_ptr), self._p(csr.ids), csr.n_units, csr.n_entries, n_kmers,
@@ -431,7 +434,7 @@ class Engine:
             counters = self._counters()
             with self._stage("pair_candidates"):
                 if use_sketch:
-                    _lib.call("cfk_pair_sketch", self._p(csr.unit_ptr), self._p(csr.ids), self._p(codes),
+                    _lib.call("cfk_pair_sketch", self._p(csr.unit_ptr), self._p(csr.ids), self._p(codes), self._p(perm),
                               self._p(unit_last), self._p(occ_ptr), self._p(occ), self._p(occ_last), csr.n_entries, n_kmers,
                               a_begin, a_end, a_stride, int(min_d), int(max_d), min_cov_u, self._p(cand), max_cand,
                               self._p(counters), self.n_sms, self._stream())

@@ -217,9 +217,16 @@ int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint
 int cfk_sketch_bits(void);
 int cfk_sketch_warps_per_block(void);
 int64_t cfk_sketch_codes_elems(int64_t n_entries, int64_t n_units);
-int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, cfk_stream_t stream);
+/* perm_ids (optional, uint32[cfk_sketch_codes_elems], 16-byte aligned, elems < 2^32): bank-aware placement.  The
+ * entries of every 128-entry block are reordered so that the byte counters a row of 32 lanes touches lie in 32
+ * different shared-memory banks wherever the block allows it (lane = bank, row = rank among the block's entries of
+ * that bank; overflow fills the free slots of the last rows), and perm_ids receives the id behind every code slot.
+ * NULL keeps the ids' own order.  Pass the same pointer (or NULL) to cfk_pair_sketch. */
+int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, uint32_t* perm_ids,
+                     cfk_stream_t stream);
 /* occ_last = cfk_occ_last output, or NULL (unit_last[g] is looked up instead). */
-int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* unit_last,
+int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* perm_ids,
+                    const uint32_t* unit_last,
                     const int64_t* occ_ptr, const uint32_t* occ, const uint32_t* occ_last, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
                     int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov,
                     uint32_t* cand, int64_t max_cand, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);

@@ -18,7 +18,7 @@ timeout -k 10 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 8
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 tail -2 gpurun_out/ncu_launches.log
 echo "== ncu full =="
-timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:'pair_sketch_kernel|docfreq_kernel|cloud_build_kernel|pair_join_kernel' -s 12 -c 4 \
+timeout -k 10 900 ncu --set full --clock-control none --import-source on -k regex:'pair_sketch_kernel|docfreq_resident_kernel|cloud_build_warp_kernel|pair_join_kernel|table_select_kernel' -s 16 -c 5 \
    -f -o gpurun_out/prof_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 ls -la gpurun_out
