@@ -288,7 +288,7 @@ def run_ours(args):
     stage_rooflines = []
     for kern, stage, nbytes, what in (
             (df_kernel, "docfreq", BYTES_PER_KMER_A * n_k, "32.25 B per k-mer occurrence"),
-            ("cloud_build_kernel", "cloud_build", 16.25 * n_ku + 4.0 * csr_last.n_entries + 8.0 * units.n_units,
+            ("cloud_build_warp_kernel", "cloud_build", 16.25 * n_ku + 4.0 * csr_last.n_entries + 8.0 * units.n_units,
              "16.25 B per k-mer inside a unit + 4 B per cloud entry + 8 B per unit"),
             ("pair_join_kernel", "pair_join", 32.0 * last.n_pair_candidates + 16.0 * int(last.edges.shape[0]),
              "32 B per pair candidate + 16 B per edge")) if world == 1 else ():
