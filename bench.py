@@ -211,9 +211,16 @@ def run_ours(args):
                                    PARAMS["min_coverage"])
         reads = eng.upload_reads(batch, k)
         dunits = eng.upload_units(units, k)
-        index, csr, res = device_step(reads, dunits)
-        out = eng.to_host(selected=res.selected, edges=res.edges, unit_ptr=csr.unit_ptr, ids=csr.ids,
-                          rare_keys=index.sorted_keys)  # pinned result buffers; synchronises
+        early = {}
+        # the rare set and the clouds are final after stage B: they travel to the host on a side stream while the
+        # distance graph is computed; edges and endpoints follow when it is done
+        index, csr, res = eng.recruit(reads, dunits, k, lo, hi, PARAMS["max_nonuniq"], PARAMS["min_d"], PARAMS["max_d"],
+                                      PARAMS["min_coverage"],
+                                      on_clouds=lambda index, csr: early.update(eng.start_host_copy(
+                                          unit_ptr=csr.unit_ptr, ids=csr.ids, rare_keys=index.sorted_keys)))
+        out = eng.to_host(selected=res.selected, edges=res.edges)  # pinned result buffers; synchronises
+        eng.finish_host_copies()
+        out.update(early)
         d2h = sum(t.numel() * t.element_size() for t in out.values())
         return reads.h2d_bytes + dunits.h2d_bytes, d2h
 

@@ -1975,33 +1975,30 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
       // row reads the null byte).  Non-flagged entries of one unit have distinct hashes, so all stores of a step hit
       // distinct bytes: plain ld/st.
       const uint32_t rem = e - p;
-      bool h0, h1 = false, h2 = false, h3 = false;
+      uint32_t o0, o1 = 0, o2 = 0, o3 = 0;  // counters before this unit's increment (0 for the rows not run)
       {
         const uint32_t a0 = tbase + (w.x & SK_OFF_MASK);
-        const uint32_t o0 = lds_u8(a0);
+        o0 = lds_u8(a0);
         if (!(w.x & SK_DUP)) sts_u8(a0, min(o0 + 1u, 255u));
-        h0 = o0 >= thr;
       }
       if (rem > 32u) {
         const uint32_t a1 = tbase + ((w.x >> 16) & SK_OFF_MASK);
-        const uint32_t o1 = lds_u8(a1);
+        o1 = lds_u8(a1);
         if ((int32_t)w.x >= 0) sts_u8(a1, min(o1 + 1u, 255u));
-        h1 = o1 >= thr;
         if (rem > 64u) {
           const uint32_t a2 = tbase + (w.y & SK_OFF_MASK);
-          const uint32_t o2 = lds_u8(a2);
+          o2 = lds_u8(a2);
           if (!(w.y & SK_DUP)) sts_u8(a2, min(o2 + 1u, 255u));
-          h2 = o2 >= thr;
           if (rem > 96u) {
             const uint32_t a3 = tbase + ((w.y >> 16) & SK_OFF_MASK);
-            const uint32_t o3 = lds_u8(a3);
+            o3 = lds_u8(a3);
             if ((int32_t)w.y >= 0) sts_u8(a3, min(o3 + 1u, 255u));
-            h3 = o3 >= thr;
           }
         }
       }
-      if (__any_sync(FULL, h0 | h1 | h2 | h3)) {
-        const bool hs[4] = {h0, h1, h2, h3};
+      // one test for the common case "nothing hot in this step"
+      if (__any_sync(FULL, max(max(o0, o1), max(o2, o3)) >= thr)) {
+        const bool hs[4] = {o0 >= thr, o1 >= thr, o2 >= thr, o3 >= thr};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const unsigned bal = __ballot_sync(FULL, hs[i]);

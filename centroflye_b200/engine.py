@@ -111,6 +111,7 @@ class Engine:
             raise CfkError(f"CFK_DOCFREQ_MODE must be resident or tiled, got {self.docfreq_mode!r}")
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
         self._host_pool = {}  # name -> pinned uint8 buffer for results (to_host)
+        self._copy_stream = None  # side stream of start_host_copy
 
     # ---- plumbing ---------------------------------------------------------------------------
     def _stream(self):
@@ -152,6 +153,35 @@ class Engine:
             out[name] = dst
         t.cuda.current_stream(self.device).synchronize()
         return out
+
+    def start_host_copy(self, **tensors):
+        """Like to_host(), but on a side stream and without waiting: the copies start as soon as the work already
+        enqueued on the current stream has produced the tensors, and overlap whatever is enqueued afterwards
+        (the cloud CSR goes home while stage C runs).  finish_host_copies() waits for them."""
+        t = self.torch
+        if self._copy_stream is None:
+            self._copy_stream = t.cuda.Stream(self.device)
+        ready = t.cuda.Event()
+        ready.record(t.cuda.current_stream(self.device))
+        self._copy_stream.wait_event(ready)
+        out = {}
+        with t.cuda.stream(self._copy_stream):
+            for name, src in tensors.items():
+                src = src.contiguous()
+                src.record_stream(self._copy_stream)
+                nbytes = src.numel() * src.element_size()
+                buf = self._host_pool.get(name)
+                if buf is None or buf.numel() < nbytes:
+                    buf = t.empty(max(nbytes + nbytes // 8, 1 << 16), dtype=t.uint8, pin_memory=True)
+                    self._host_pool[name] = buf
+                dst = buf[:nbytes].view(src.dtype).view(src.shape)
+                dst.copy_(src, non_blocking=True)
+                out[name] = dst
+        return out
+
+    def finish_host_copies(self):
+        if self._copy_stream is not None:
+            self._copy_stream.synchronize()
 
     def _empty(self, n, dtype):
         return self.torch.empty(max(int(n), 1), dtype=dtype, device=self.device)
@@ -480,13 +510,17 @@ class Engine:
 
     # ---- whole path -------------------------------------------------------------------------
     def recruit(self, reads, units, k, lo, hi, max_nonuniq, min_d, max_d, min_cov, rel_threshold=0.8,
-                unit_lo=0, unit_hi=None):
-        """main() of the reference script on device-resident inputs; returns device-resident results."""
+                unit_lo=0, unit_hi=None, on_clouds=None):
+        """main() of the reference script on device-resident inputs; returns device-resident results.
+        on_clouds(index, csr) is called as soon as the rare set and the clouds are final (before the distance graph):
+        the place to start their trip to the host (start_host_copy)."""
         table = self.count_docfreq(reads, k)
         rare = self.table_select(table, lo, hi, max_nonuniq)
         del table
         index = self.build_index(rare)
         csr = self.build_clouds(reads, units, k, index)
+        if on_clouds is not None:
+            on_clouds(index, csr)
         dist = self.dist_edges(csr, units.unit_last, index.n, min_d, max_d, min_cov, rel_threshold,
                                unit_lo=unit_lo, unit_hi=unit_hi)
         return index, csr, dist
