@@ -251,8 +251,14 @@ docfreq_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ 
 // Reads too long to leave DF3_MIN_SET slots keep their words in global memory (same code, other
 // address space).
 // --------------------------------------------------------------------------------------------
-constexpr int DF3_SMEM_WORDS = 57344;  // 224 KB of dynamic shared memory
-constexpr int DF3_MIN_SET = 16384;
+#ifndef CFK_DF3_THREADS
+#define CFK_DF3_THREADS 1024  /* threads per block; 1024 / this many blocks share an SM and its shared memory */
+#endif
+constexpr int DF3_THREADS = CFK_DF3_THREADS;
+constexpr int DF3_BLOCKS_PER_SM = 1024 / DF3_THREADS;
+static_assert(DF3_THREADS == 1024 || DF3_THREADS == 512 || DF3_THREADS == 256, "1, 2 or 4 blocks per SM");
+constexpr int DF3_SMEM_WORDS = DF3_BLOCKS_PER_SM == 1 ? 57344 : 57344 / DF3_BLOCKS_PER_SM - 512;  // dynamic shared memory of a block
+constexpr int DF3_MIN_SET = 16384 / DF3_BLOCKS_PER_SM;
 #ifndef CFK_DF3_FILL_PCT
 #define CFK_DF3_FILL_PCT 53   /* planned load of the per-read set, percent */
 #endif
@@ -442,7 +448,7 @@ __device__ __forceinline__ void df3_fetch(const int64_t* __restrict__ item_ptr, 
   *s_read = idx;
 }
 
-__global__ void __launch_bounds__(DF_THREADS, 1)
+__global__ void __launch_bounds__(DF3_THREADS, DF3_BLOCKS_PER_SM)
 docfreq_resident_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ read_off,
                         const int64_t* __restrict__ read_len, const int32_t* __restrict__ order,
                         const int64_t* __restrict__ item_ptr, int64_t n_reads, int k, uint64_t* table, int64_t cap,
@@ -463,12 +469,12 @@ docfreq_resident_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
     const Df3Geometry g = df3_geometry(len);
     uint32_t* set = df_smem + g.n_words;
     const uint32_t c_eff = (n_pass > 1) ? g.set_slots : (uint32_t)min((int64_t)g.set_slots, max((int64_t)2048, (nk * 100 / CFK_DF3_FILL_PCT + 7) & ~(int64_t)3));
-    for (uint32_t i = threadIdx.x * 4; i < c_eff; i += DF_THREADS * 4)  // n_words and c_eff are multiples of 4
+    for (uint32_t i = threadIdx.x * 4; i < c_eff; i += DF3_THREADS * 4)  // n_words and c_eff are multiples of 4
       *reinterpret_cast<uint4*>(set + i) = make_uint4(0, 0, 0, 0);
     if (g.n_words) {
       const uint32_t real_words = (uint32_t)((len + 15) >> 4);  // 16-byte loads stay inside the read's own 64-base blocks
       const uint32_t real_quads = (real_words + 3) >> 2;
-      for (uint32_t i = threadIdx.x; i < g.n_words / 4; i += DF_THREADS) {
+      for (uint32_t i = threadIdx.x; i < g.n_words / 4; i += DF3_THREADS) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if (i < real_quads) v = __ldg(reinterpret_cast<const uint4*>(gwords) + i);
         *reinterpret_cast<uint4*>(df_smem + 4 * i) = v;
@@ -2215,7 +2221,7 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
     if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_docfreq_count_resident: cudaFuncSetAttribute", e);
     attr_done = true;
   }
-  docfreq_resident_kernel<<<(unsigned)n_blocks, DF_THREADS, smem, (cudaStream_t)stream>>>(
+  docfreq_resident_kernel<<<(unsigned)n_blocks * DF3_BLOCKS_PER_SM, DF3_THREADS, smem, (cudaStream_t)stream>>>(
       packed, read_off, read_len, order, item_ptr, n_reads, k, table, cap, counters);
   CFK_CHECK_LAUNCH("docfreq_resident_kernel", 1);
   return CFK_OK;
