@@ -507,6 +507,28 @@ __global__ void table_merge_kernel(const uint64_t* __restrict__ keys, const uint
   if (nmulti[i]) atomicAdd(cnt + 1, nmulti[i]);
 }
 
+// counts of n given keys (0 / 0 for a key the table does not hold)
+__global__ void table_lookup_kernel(const uint64_t* __restrict__ table, int64_t cap, const uint64_t* __restrict__ keys, int64_t n,
+                                    uint32_t* __restrict__ out_nreads, uint32_t* __restrict__ out_nmulti) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = keys[i];
+  int64_t slot = home_slot(mix64(key), cap);
+  uint32_t nr = 0, nm = 0;
+  for (int64_t probes = 0; probes < cap; ++probes) {
+    const ulonglong2 sl = __ldg(reinterpret_cast<const ulonglong2*>(table) + slot);
+    if (sl.x == key) {
+      nr = (uint32_t)sl.y;
+      nm = (uint32_t)(sl.y >> 32);
+      break;
+    }
+    if (sl.x == EMPTY) break;
+    if (++slot == cap) slot = 0;
+  }
+  out_nreads[i] = nr;
+  out_nmulti[i] = nm;
+}
+
 // warp-aggregated append: returns the output position of this lane's item, or -1
 __device__ __forceinline__ int64_t warp_append(bool take, int64_t* counter) {
   unsigned m = __ballot_sync(FULL, take);
@@ -523,28 +545,66 @@ __device__ __forceinline__ int32_t key_owner(uint64_t key, int32_t n_parts) {
   return (int32_t)(mix64(key ^ 0x9E3779B97F4A7C15ull) % (uint64_t)n_parts);
 }
 
-__global__ void table_select_kernel(const uint64_t* __restrict__ table, int64_t cap, uint32_t lo, uint32_t hi,
-                                    uint32_t max_nonuniq, int32_t n_parts, int32_t part, uint64_t* out_keys,
-                                    uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out, int64_t* counters) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool take = false;
-  uint64_t key = 0;
-  uint32_t nr = 0, nm = 0;
-  if (i < cap) {
-    const ulonglong2 s = reinterpret_cast<const ulonglong2*>(table)[i];
-    key = s.x;
+// One block = SEL_THREADS x SEL_ITEMS consecutive slots and ONE atomicAdd on the output cursor (a warp-level append costs
+// an atomic per warp with a match: 3 million serialised atomics on one address when 1 % of the slots match).
+constexpr int SEL_THREADS = 256;
+#ifndef CFK_SEL_ITEMS
+#define CFK_SEL_ITEMS 2
+#endif
+constexpr int SEL_ITEMS = CFK_SEL_ITEMS;
+
+__global__ void __launch_bounds__(SEL_THREADS)
+table_select_kernel(const uint64_t* __restrict__ table, int64_t cap, uint32_t lo, uint32_t hi, uint32_t max_nonuniq,
+                    int32_t n_parts, int32_t part, uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti,
+                    int64_t max_out, int64_t* counters) {
+  __shared__ int s_warp[SEL_THREADS / 32];
+  __shared__ long long s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t first = (int64_t)blockIdx.x * (SEL_THREADS * SEL_ITEMS) + threadIdx.x;
+  ulonglong2 slot[SEL_ITEMS];
+  uint32_t takes = 0;
+#pragma unroll
+  for (int it = 0; it < SEL_ITEMS; ++it) {
+    const int64_t i = first + (int64_t)it * SEL_THREADS;
+    slot[it] = make_ulonglong2(EMPTY, 0ull);
+    if (i < cap) slot[it] = __ldg(reinterpret_cast<const ulonglong2*>(table) + i);
+    const uint64_t key = slot[it].x;
     if (key != EMPTY) {
-      nr = (uint32_t)s.y;
-      nm = (uint32_t)(s.y >> 32);
-      take = nm <= max_nonuniq && nr >= lo && nr <= hi;
+      const uint32_t nr = (uint32_t)slot[it].y, nm = (uint32_t)(slot[it].y >> 32);
+      bool take = nm <= max_nonuniq && nr >= lo && nr <= hi;
       if (take && n_parts > 0) take = key_owner(key, n_parts) == part;
+      takes |= (uint32_t)take << it;
     }
   }
-  int64_t pos = warp_append(take, counters);
-  if (take && pos < max_out) {
-    if (out_keys) out_keys[pos] = key;
-    if (out_nreads) out_nreads[pos] = nr;
-    if (out_nmulti) out_nmulti[pos] = nm;
+  // block-exclusive scan of the per-thread match counts
+  const int mine = __popc(takes);
+  int incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int w = 0; w < SEL_THREADS / 32; ++w) {
+      const int c = s_warp[w];
+      s_warp[w] = total;
+      total += c;
+    }
+    s_base = total ? (long long)atomicAdd((unsigned long long*)counters, (unsigned long long)total) : 0ll;
+  }
+  __syncthreads();
+  int64_t pos = (int64_t)s_base + s_warp[warp] + incl - mine;
+#pragma unroll
+  for (int it = 0; it < SEL_ITEMS; ++it) {
+    if (!((takes >> it) & 1u)) continue;
+    if (pos < max_out) {
+      if (out_keys) out_keys[pos] = slot[it].x;
+      if (out_nreads) out_nreads[pos] = (uint32_t)slot[it].y;
+      if (out_nmulti) out_nmulti[pos] = (uint32_t)(slot[it].y >> 32);
+    }
+    ++pos;
   }
 }
 
@@ -2237,12 +2297,21 @@ int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t
   return CFK_OK;
 }
 
+int cfk_table_lookup(const uint64_t* table, int64_t cap, const uint64_t* keys, int64_t n, uint32_t* out_nreads,
+                     uint32_t* out_nmulti, cfk_stream_t stream) {
+  if (n < 0 || cap < 1) return fail(CFK_ERR_INVALID, "cfk_table_lookup: bad sizes");
+  if (n == 0) return CFK_OK;
+  table_lookup_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(table, cap, keys, n, out_nreads, out_nmulti);
+  CFK_CHECK_LAUNCH("table_lookup_kernel", 1);
+  return CFK_OK;
+}
+
 int cfk_table_select(const uint64_t* table, int64_t cap, uint32_t lo, uint32_t hi, uint32_t max_nonuniq, int32_t n_parts,
                      int32_t part, uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out,
                      int64_t* counters, cfk_stream_t stream) {
   if (cap < 1 || max_out < 0) return fail(CFK_ERR_INVALID, "cfk_table_select: bad sizes");
   if (n_parts > 0 && (part < 0 || part >= n_parts)) return fail(CFK_ERR_INVALID, "cfk_table_select: bad partition");
-  table_select_kernel<<<(unsigned)blocks_for(cap, 256), 256, 0, (cudaStream_t)stream>>>(
+  table_select_kernel<<<(unsigned)blocks_for(cap, SEL_THREADS * SEL_ITEMS), SEL_THREADS, 0, (cudaStream_t)stream>>>(
       table, cap, lo, hi, max_nonuniq, n_parts, part, out_keys, out_nreads, out_nmulti, max_out, counters);
   CFK_CHECK_LAUNCH("table_select_kernel", 1);
   return CFK_OK;

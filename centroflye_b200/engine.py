@@ -305,6 +305,15 @@ class Engine:
             return keys[:n], nreads[:n], nmulti[:n]
         return keys[:n]
 
+    def table_lookup(self, table, keys):
+        """(n_reads, n_multi) int32 tensors of the given keys (0 / 0 where the table does not hold the key)."""
+        t = self.torch
+        n = int(keys.numel())
+        nreads, nmulti = self._empty(n, t.int32), self._empty(n, t.int32)
+        _lib.call("cfk_table_lookup", self._p(table.slots), table.cap, self._p(keys.contiguous()), n, self._p(nreads),
+                  self._p(nmulti), self._stream())
+        return nreads[:n], nmulti[:n]
+
     def part_count(self, table, n_parts):
         """int64[n_parts] (device): occupied slots per hash partition (owner = mix64(key ^ golden) % n_parts)."""
         counts = self._zeros(n_parts, self.torch.int64)

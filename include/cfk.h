@@ -113,6 +113,12 @@ int cfk_table_select(const uint64_t* table, int64_t cap, uint32_t lo, uint32_t h
                      int32_t part, uint64_t* out_keys, uint32_t* out_nreads, uint32_t* out_nmulti, int64_t max_out,
                      int64_t* counters, cfk_stream_t stream);
 
+/* (n_reads, n_multi) of n given keys, 0 / 0 for keys the table does not hold: the per-rank half of the multi-GPU
+ * "nominate, then sum" exchange: only k-mers that reach ceil(lo / G) reads on SOME rank can reach
+ * lo reads in total, so only those are looked up on every rank and summed. */
+int cfk_table_lookup(const uint64_t* table, int64_t cap, const uint64_t* keys, int64_t n, uint32_t* out_nreads,
+                     uint32_t* out_nmulti, cfk_stream_t stream);
+
 /* Hash partition of a whole table for the multi-GPU exchange: every occupied
  * slot goes to partition owner(key) = mix64(key ^ 0x9E3779B97F4A7C15) % n_parts (the rule
  * cfk_table_select applies), n_parts <= 64.  cfk_table_part_count adds the partition sizes to

@@ -76,6 +76,24 @@ def _worker(rank, world, port, out_dir):
         want_rare = gk[(gm <= max_nonuniq) & (gr >= lo) & (gr <= hi)]
         assert rare.size > 50 and np.array_equal(rare, want_rare)
 
+        # --- nominate-then-sum (ShardedRecruiter.global_rare_keys): same rare set for ~1 % of the traffic --------------
+        import torch.distributed as tdist
+        for lo2, hi2 in ((3, 12), (4, 9), (7, 40)):
+            share = -(-lo2 // world)
+            assert share >= 2
+            nominated = keys[nr >= share]
+            allk, _ = cdist.all_gather_v(torch.from_numpy(nominated.view(np.int64)))
+            union = torch.unique(allk).numpy().view(np.uint64)
+            pos = np.searchsorted(keys, union)
+            pos_c = np.minimum(pos, max(keys.size - 1, 0))
+            held = (pos < keys.size) & (keys[pos_c] == union)
+            sums = torch.from_numpy(np.stack([np.where(held, nr[pos_c], 0), np.where(held, nm[pos_c], 0)]).astype(np.int64))
+            tdist.all_reduce(sums)
+            sums = sums.numpy()
+            got2 = union[(sums[0] >= lo2) & (sums[0] <= hi2) & (sums[1] <= max_nonuniq)]
+            assert np.array_equal(got2, gk[(gm <= max_nonuniq) & (gr >= lo2) & (gr <= hi2)])
+            assert nominated.size < keys.size
+
         # --- all-gathered cloud shards + round-robin sources == whole graph ----------------------------------
         ptr, ids = c_oracle.clouds(c_oracle.unpacked_codes(my_batch), my_units, k, rare)
         cnt_all, unit_counts = cdist.all_gather_v(torch.from_numpy(np.diff(ptr).astype(np.int32)))
