@@ -201,7 +201,8 @@ def run_ours(args):
 
     def device_step(reads, dunits):
         if runner is not None:
-            return runner.step(lo, hi, PARAMS["max_nonuniq"], PARAMS["min_d"], PARAMS["max_d"], PARAMS["min_coverage"])
+            return runner.step(lo, hi, PARAMS["max_nonuniq"], PARAMS["min_d"], PARAMS["max_d"], PARAMS["min_coverage"],
+                               gather=False)  # edges stay sharded by source k-mer, like the work
         return eng.recruit(reads, dunits, k, lo, hi, PARAMS["max_nonuniq"], PARAMS["min_d"], PARAMS["max_d"],
                            PARAMS["min_coverage"])
 
@@ -262,6 +263,11 @@ def run_ours(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
     last = res[2]
+    n_edges_total = int(last.edges.shape[0])
+    if world > 1:
+        ne = torch.tensor([n_edges_total], dtype=torch.int64, device=eng.device)
+        dist.all_reduce(ne)
+        n_edges_total = int(ne.item())
 
     # end to end: pinned host buffers -> host results, same call
     e2e_ms, h2d, d2h = [], 0, 0
@@ -277,6 +283,9 @@ def run_ours(args):
         tms = torch.tensor([e2e], device=eng.device)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         e2e = float(tms.item())
+        nbytes = torch.tensor([h2d, d2h], dtype=torch.int64, device=eng.device)  # every rank moves its own shard
+        dist.all_reduce(nbytes)
+        h2d, d2h = int(nbytes[0].item()), int(nbytes[1].item())
 
     if rank != 0:
         return
@@ -317,10 +326,11 @@ def run_ours(args):
                                   if world > 1 else ""),
                    "scale": args.scale, "read_bases": int(n_bases_total), "reads_rank0": int(batch.n_reads),
                    "units_rank0": int(units.n_units), "pair_increments": int(n_incr),
-                   "candidates": int(last.n_candidates), "pair_candidates": int(last.n_pair_candidates), "edges": int(last.edges.shape[0]),
+                   "candidates": int(last.n_candidates), "pair_candidates": int(last.n_pair_candidates), "edges": n_edges_total,
                    "unique_kmers": int(last.selected.numel()), "l2": "256 MiB flush write between timed steps",
-                   "sharding": ("reads sharded by record; all-to-all of (k-mer, n_reads, n_multi) records, all-gather of rare "
-                                "keys and cloud CSR, sources dealt round-robin" if world > 1 else "single GPU")},
+                   "sharding": ("reads sharded by record; stage A: nominate-then-sum (all-gather of the k-mers with >= "
+                                "ceil(lo/N) local reads, one all-reduce of their counts); cloud CSR all-gathered; source "
+                                "k-mers dealt round-robin, edges stay with their source's rank" if world > 1 else "single GPU")},
         "roofline": {"kernel": pair_kernel, "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": dc_ms,

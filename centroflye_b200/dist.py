@@ -179,10 +179,12 @@ class ShardedRecruiter:
                          device=eng.device)
         self.dist.all_reduce(stats, group=self.group)
         self.last_increments = int(stats[0].item())
-        if not gather:
-            return index, csr, res
         with eng._stage("gather_edges"):
-            edges, _ = all_gather_v(res.edges.reshape(-1).contiguous(), self.group)
+            # the recruited k-mers (endpoints of kept edges) are the union over ranks: every rank gets all of them;
+            # the edges themselves stay sharded by source k-mer (rank r holds the sources a = r mod G) unless gather
+            edges = res.edges.reshape(-1)
+            if gather:
+                edges, _ = all_gather_v(edges.contiguous(), self.group)
             flags = eng._zeros(index.n, t.int32)
             if res.selected.numel():
                 flags[res.selected.to(t.int64)] = 1
@@ -194,14 +196,16 @@ class ShardedRecruiter:
         return index, csr, out
 
     def e2e_step(self, lo, hi, max_nonuniq, min_d, max_d, min_cov):
-        """Pinned host buffers -> host results (rank 0 reads edges / endpoints, every rank its own clouds)."""
+        """Pinned host buffers -> host results, sharded like the work: every rank reads back its own clouds and the
+        edges of its own source k-mers; rank 0 also the recruited k-mers and the rare set.  Returns this rank's
+        (h2d, d2h) bytes."""
         eng = self.eng
         self.reads = eng.upload_reads(self.batch, self.k)
         self.dunits = eng.upload_units(self.units, self.k)
-        index, csr, res = self.step(lo, hi, max_nonuniq, min_d, max_d, min_cov)
-        want = dict(unit_ptr=csr.unit_ptr, ids=csr.ids)
+        index, csr, res = self.step(lo, hi, max_nonuniq, min_d, max_d, min_cov, gather=False)
+        want = dict(unit_ptr=csr.unit_ptr, ids=csr.ids, edges=res.edges)
         if self.rank == 0:
-            want.update(selected=res.selected, edges=res.edges, rare_keys=index.sorted_keys)
+            want.update(selected=res.selected, rare_keys=index.sorted_keys)
         out = eng.to_host(**want)  # pinned result buffers; synchronises
         d2h = sum(x.numel() * x.element_size() for x in out.values())
         return self.reads.h2d_bytes + self.dunits.h2d_bytes, d2h
