@@ -1788,6 +1788,12 @@ __device__ __forceinline__ uint32_t join_candidate(bool active, uint4 c, const J
 // exact tables.  A pass whose set overflows is abandoned before anything is emitted and redone
 // over fewer distances / a narrower id range.
 // ============================================================================================
+#ifndef CFK_SKETCH_ALL_ROWS
+#define CFK_SKETCH_ALL_ROWS 1
+#endif
+#ifndef CFK_SKETCH_CACHED
+#define CFK_SKETCH_CACHED 1 /* per-source occurrence + unit_ptr window kept in registers (sources with <= 32 occurrences) */
+#endif
 constexpr int SK_BITS = CFK_SKETCH_BITS;
 constexpr int SK_TBL_BYTES = 1 << SK_BITS;
 constexpr uint32_t SK_OFF_MASK = 0x3FFFu;          // code bits 0..13: byte offset in the warp's table (hash, or the null byte)
@@ -1954,7 +1960,22 @@ struct SketchArgs {
   uint4* cand;
   int64_t max_cand;
   int64_t* counters;
+  struct SketchChunk* chunk;  // the warp's current chunk of cand[]
 };
+
+constexpr int SK_CAND_CHUNK = 256;
+constexpr uint32_t SK_NO_CAND = 0xFFFFFFFFu;  // a = 0xFFFFFFFF: hole at the end of a chunk (cfk_pair_join skips it)
+struct SketchChunk {
+  int64_t pos, end, emitted;
+};
+
+// the unused tail of the warp's chunk becomes holes
+__device__ __forceinline__ void sk_close_chunk(const SketchArgs& A) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t q = A.chunk->pos + lane; q < A.chunk->end; q += 32)
+    if (q < A.max_cand) A.cand[q] = make_uint4(SK_NO_CAND, 0u, 0u, 0u);
+  A.chunk->pos = A.chunk->end;
+}
 
 // queued hot positions -> level-2 set.  Returns false if the set overflowed.
 __device__ bool sk_drain(uint32_t l2base, uint32_t qbase, const SketchArgs& A, int qn, int64_t lo_id, int64_t hi_id,
@@ -1989,11 +2010,37 @@ __device__ bool sk_drain(uint32_t l2base, uint32_t qbase, const SketchArgs& A, i
 
 // One pass: distances d0 .. d0 + nd - 1, hot ids restricted to [lo_id, hi_id).  Returns the number
 // of candidates emitted, or -1 if the level-2 set overflowed (nothing emitted).
-__device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, int64_t lo_id, int64_t hi_id) {
+// pre != nullptr (sources with at most 32 occurrences, one distance per pass): lane t already holds its unit g_t + d0 as
+// (first entry, end entry, unit index) -- sketch_source keeps a sliding window of unit_ptr values in registers, so the
+// pass starts without a single dependent load.
+struct SketchPre {
+  uint32_t up, ue;
+  int64_t unit;
+};
+
+__device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, int64_t lo_id, int64_t hi_id,
+                           const SketchPre* pre = nullptr) {
   const int lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
   const uint32_t l2base = tbase + SK_TBL_BYTES + SK_PAD_BYTES, qbase = l2base + SK_L2_SLOTS * 4;
   const uint32_t thr = A.thr;
+  uint32_t up = 0, ue = 0, ub = 0;  // this lane's unit: entries [up, ue) of ids[], first block of codes[]
+  unsigned rest = 0;
+  int src = 0;
+  uint32_t p = 0, e = 0, cb = 0;
+  uint2 w = make_uint2(0, 0);
+  if (pre != nullptr) {  // the units are known: the first code block is requested before the table is cleared
+    up = pre->up;
+    ue = pre->ue;
+    ub = (uint32_t)sk_block((int64_t)up, pre->unit);
+    rest = __ballot_sync(FULL, ue > up);
+    if (rest) {
+      src = __ffs(rest) - 1;
+      rest &= rest - 1;
+      p = __shfl_sync(FULL, up, src); e = __shfl_sync(FULL, ue, src); cb = __shfl_sync(FULL, ub, src);
+      w = __ldg(A.codes + (size_t)cb * 32u + lane);
+    }
+  }
 #pragma unroll 4
   for (int i = lane; i < (SK_TBL_BYTES + SK_PAD_BYTES + SK_L2_SLOTS * 4) / 16; i += 32)
     sts128(tbase + (uint32_t)i * 16u, make_uint4(0, 0, 0, 0));
@@ -2001,28 +2048,46 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
   int qn = 0, claims = 0;
   const int64_t n_items = A.m * (int64_t)nd;
   for (int64_t i0 = 0; i0 < n_items; i0 += 32) {
-    const int64_t it = i0 + lane;
-    uint32_t up = 0, ue = 0, ub = 0;  // this lane's unit: entries [up, ue) of ids[], first block of codes[]
-    if (it < n_items) {
-      const int64_t t = (nd == 1) ? it : it / nd;
-      const int64_t g = (int64_t)__ldg(A.occ_a + t);
-      const int64_t u = g + d0 + (it - t * nd);
-      if (u <= last_unit_of(A.unit_last, A.last_a, t, g)) {
-        const int64_t p0 = __ldg(A.unit_ptr + u);
-        up = (uint32_t)p0;
-        ue = (uint32_t)__ldg(A.unit_ptr + u + 1);
-        ub = (uint32_t)sk_block(p0, u);
+    if (pre != nullptr) {
+      if (e <= p) continue;  // no occurrence has a unit at this distance (one group only: m <= 32)
+    } else {
+      const int64_t it = i0 + lane;
+      up = 0; ue = 0; ub = 0;
+      if (it < n_items) {
+        const int64_t t = (nd == 1) ? it : it / nd;
+        const int64_t g = (int64_t)__ldg(A.occ_a + t);
+        const int64_t u = g + d0 + (it - t * nd);
+        if (u <= last_unit_of(A.unit_last, A.last_a, t, g)) {
+          const int64_t p0 = __ldg(A.unit_ptr + u);
+          up = (uint32_t)p0;
+          ue = (uint32_t)__ldg(A.unit_ptr + u + 1);
+          ub = (uint32_t)sk_block(p0, u);
+        }
       }
+      rest = __ballot_sync(FULL, ue > up);
+      if (!rest) continue;
+      src = __ffs(rest) - 1;
+      rest &= rest - 1;
+      p = __shfl_sync(FULL, up, src); e = __shfl_sync(FULL, ue, src); cb = __shfl_sync(FULL, ub, src);
+      w = __ldg(A.codes + (size_t)cb * 32u + lane);
     }
-    unsigned rest = __ballot_sync(FULL, ue > up);
-    if (!rest) continue;
-    int src = __ffs(rest) - 1;
-    rest &= rest - 1;
-    uint32_t p = __shfl_sync(FULL, up, src), e = __shfl_sync(FULL, ue, src), cb = __shfl_sync(FULL, ub, src);
-    uint2 w = __ldg(A.codes + (size_t)cb * 32u + lane);
     for (;;) {
       // the next window (rest of this unit, else the next unit of the group): its codes fly during this step
       uint32_t np = p + SK_WINDOW, ne = e, ncb = cb + 1u;
+#if CFK_SKETCH_ALL_ROWS
+      // branch-free: the next unit's descriptor is fetched whether or not this unit is finished (it is, four steps out
+      // of five), so that the bookkeeping shares one basic block with the rows below
+      const bool sw = np >= ne;  // warp-uniform
+      const int nsrc = (__ffs(rest) - 1) & 31;
+      const uint32_t sp = __shfl_sync(FULL, up, nsrc), se = __shfl_sync(FULL, ue, nsrc), sb = __shfl_sync(FULL, ub, nsrc);
+      const bool more = !sw || rest != 0u;
+      np = sw ? sp : np;
+      ne = sw ? se : ne;
+      ncb = sw ? sb : ncb;
+      rest = sw ? (rest & (rest - 1u)) : rest;
+      uint2 nw = make_uint2(0, 0);
+      if (more) nw = __ldg(A.codes + (size_t)ncb * 32u + lane);
+#else
       bool more = true;
       if (np >= ne) {
         if (rest) {
@@ -2037,9 +2102,22 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
       }
       uint2 nw = make_uint2(0, 0);
       if (more) nw = __ldg(A.codes + (size_t)ncb * 32u + lane);
+#endif
       // level 1, one row of 32 entries at a time (rows behind the end of the unit are skipped; padding inside the last
       // row reads the null byte).  Non-flagged entries of one unit have distinct hashes, so all stores of a step hit
       // distinct bytes: plain ld/st.
+#if CFK_SKETCH_ALL_ROWS
+      // all four rows, unconditionally: the slots behind the end of a unit hold null codes (they read an always-zero pad
+      // word and do not store), and without the per-row branches the four load / add / store chains are one basic block
+      // that the scheduler interleaves -- with 5.5 warps per scheduler the fixed ALU latencies are the top stall
+      const uint32_t a0 = tbase + (w.x & SK_OFF_MASK), a1 = tbase + ((w.x >> 16) & SK_OFF_MASK);
+      const uint32_t a2 = tbase + (w.y & SK_OFF_MASK), a3 = tbase + ((w.y >> 16) & SK_OFF_MASK);
+      const uint32_t o0 = lds_u8(a0), o1 = lds_u8(a1), o2 = lds_u8(a2), o3 = lds_u8(a3);
+      if (!(w.x & SK_DUP)) sts_u8(a0, min(o0 + 1u, 255u));
+      if ((int32_t)w.x >= 0) sts_u8(a1, min(o1 + 1u, 255u));
+      if (!(w.y & SK_DUP)) sts_u8(a2, min(o2 + 1u, 255u));
+      if ((int32_t)w.y >= 0) sts_u8(a3, min(o3 + 1u, 255u));
+#else
       const uint32_t rem = e - p;
       uint32_t o0, o1 = 0, o2 = 0, o3 = 0;  // counters before this unit's increment (0 for the rows not run)
       {
@@ -2062,6 +2140,7 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
           }
         }
       }
+#endif
       // one test for the common case "nothing hot in this step"
       if (__any_sync(FULL, max(max(o0, o1), max(o2, o3)) >= thr)) {
         const bool hs[4] = {o0 >= thr, o1 >= thr, o2 >= thr, o3 >= thr};
@@ -2091,8 +2170,24 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const bool take = w[j] != 0u;
-        const int64_t pos = warp_append(take, A.counters);
-        if (take && pos < A.max_cand) A.cand[pos] = make_uint4(A.a, w[j] - 1u, (uint32_t)d0, (uint32_t)(d0 + nd - 1));
+        const unsigned bal = __ballot_sync(FULL, take);
+        if (bal) {
+          // the warp owns a chunk of the candidate array and fills it without atomics; one atomicAdd on the (single,
+          // contended) cursor per SK_CAND_CHUNK candidates instead of one round trip per pass
+          const int n = __popc(bal);
+          if (A.chunk->pos + n > A.chunk->end) {
+            sk_close_chunk(A);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd((unsigned long long*)A.counters, (unsigned long long)SK_CAND_CHUNK);
+            base = __shfl_sync(FULL, base, 0);
+            A.chunk->pos = (int64_t)base;
+            A.chunk->end = (int64_t)base + SK_CAND_CHUNK;
+          }
+          const int64_t pos = A.chunk->pos + __popc(bal & lt);
+          if (take && pos < A.max_cand) A.cand[pos] = make_uint4(A.a, w[j] - 1u, (uint32_t)d0, (uint32_t)(d0 + nd - 1));
+          A.chunk->pos += n;
+          A.chunk->emitted += n;
+        }
         emitted += take;
       }
     }
@@ -2105,6 +2200,35 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
   const int lane = threadIdx.x & 31;
   int d0 = dmin;
   int nd_force = SK_ND_MAX;
+#if CFK_SKETCH_CACHED
+  // Sources with at most 32 occurrences (nearly all: the rare band caps the reads per k-mer): lane t keeps occurrence t
+  // -- its unit g_t and the end of its read -- and a sliding window W[i] = unit_ptr[min(g_t + d0 + i, last_t + 1)],
+  // i = 0..4, in registers.  Planning a pass (how many distances fit the sketch) and starting it then need no load at
+  // all; the one value that enters the window per distance is requested four distances before it is used.
+  const bool cached = A.m <= 32;
+  int64_t cg = 0, clim = 0;
+  uint32_t W0 = 0, W1 = 0, W2 = 0, W3 = 0, W4 = 0;
+  auto window_at = [&](int d) -> uint32_t { return lane < A.m ? (uint32_t)__ldg(A.unit_ptr + min(cg + d, clim)) : 0u; };
+  if (cached) {
+    if (lane < A.m) {
+      cg = (int64_t)__ldg(A.occ_a + lane);
+      clim = last_unit_of(A.unit_last, A.last_a, lane, cg) + 1;
+    }
+    W0 = window_at(d0); W1 = window_at(d0 + 1); W2 = window_at(d0 + 2); W3 = window_at(d0 + 3); W4 = window_at(d0 + 4);
+  }
+  auto advance_d = [&](int by) {
+    for (int i = 0; i < by; ++i) {
+      ++d0;
+      if (cached) {
+        W0 = W1; W1 = W2; W2 = W3; W3 = W4;
+        W4 = window_at(d0 + 4);
+      }
+    }
+  };
+#else
+  const bool cached = false;
+  auto advance_d = [&](int by) { d0 += by; };
+#endif
   while (d0 <= dlim) {
     // plan: extend the pass one distance at a time (4 looked up per round) while the cloud entries fit SK_CAP
     const int nd_max = min(nd_force, dlim - d0 + 1);
@@ -2113,6 +2237,11 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
     bool stop = false;
     for (int jb = 0; jb < nd_max && !stop; jb += 4) {
       uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#if CFK_SKETCH_CACHED
+      if (cached && jb == 0) {
+        c0 = W1 - W0; c1 = W2 - W1; c2 = W3 - W2; c3 = W4 - W3;
+      } else
+#endif
       for (int64_t t0 = 0; t0 < A.m; t0 += 32) {
         const int64_t t = t0 + lane;
         if (t < A.m) {
@@ -2135,12 +2264,18 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
       }
     }
     if (nd < 1) { nd = 1; tot = first; }
-    if (tot == 0) { d0 += nd; nd_force = SK_ND_MAX; continue; }
+    if (tot == 0) { advance_d(nd); nd_force = SK_ND_MAX; continue; }
     bool redo = false;
     int64_t lo_id = 0, width = A.n_kmers;
+#if CFK_SKETCH_CACHED
+    const SketchPre pre{W0, W1, cg + d0};  // W0 == W1 for the lanes without a unit at this distance
+    const SketchPre* prep = (cached && nd == 1) ? &pre : nullptr;
+#else
+    const SketchPre* prep = nullptr;
+#endif
     while (lo_id < A.n_kmers) {
       const int64_t hi_id = min(A.n_kmers, lo_id + width);
-      const int emitted = sketch_pass(tbase, A, d0, nd, lo_id, hi_id);
+      const int emitted = sketch_pass(tbase, A, d0, nd, lo_id, hi_id, prep);
       if (emitted < 0) {  // level-2 set overflow: fewer distances, then narrower id ranges
         ++splits;
         if (nd > 1) { nd_force = nd >> 1; redo = true; break; }
@@ -2151,7 +2286,7 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
       if (emitted < SK_L2_MAX / 2 && width < A.n_kmers) width <<= 1;  // sparse stretch of the id space: widen again
     }
     if (redo) continue;
-    d0 += nd;
+    advance_d(nd);
     nd_force = SK_ND_MAX;
   }
 }
@@ -2167,6 +2302,7 @@ pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restr
   const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(pc_smem) + (uint32_t)warp * SK_WARP_BYTES;
   const int dmin = max(min_d, 1);
   int64_t incr_total = 0, splits = 0;
+  SketchChunk chunk{0, 0, 0};
   for (;;) {
     unsigned long long item = 0;
     if (lane == 0) item = atomicAdd((unsigned long long*)(counters + 1), 1ull);
@@ -2181,10 +2317,18 @@ pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restr
     const int dlim = source_scope(unit_ptr, unit_last, occ_a, m, dmin, max_d, min_cov, incr_total, last_a);
     if (dlim < dmin) continue;
     SketchArgs A{unit_ptr, perm_ids ? perm_ids : ids, perm_ids != nullptr, codes, unit_last, last_a, occ_a, m, n_kmers, a, min_cov - 1u, cand,
-                 max_cand, counters};
+                 max_cand, counters, &chunk};
     sketch_source(tbase, A, dmin, dlim, splits);
   }
+  {
+    SketchArgs A{};
+    A.cand = cand;
+    A.max_cand = max_cand;
+    A.chunk = &chunk;
+    sk_close_chunk(A);
+  }
   if (lane == 0) {
+    if (chunk.emitted) atomicAdd((unsigned long long*)(counters + 4), (unsigned long long)chunk.emitted);
     if (incr_total) atomicAdd((unsigned long long*)(counters + 2), (unsigned long long)incr_total);
     if (splits) atomicAdd((unsigned long long*)(counters + 3), (unsigned long long)splits);
   }
@@ -2203,9 +2347,9 @@ __global__ void pair_join_kernel(const uint4* __restrict__ cand, int64_t n_cand,
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const JoinArgs J{occ_ptr, occ, occ_last, unit_last, (uint32_t)max(min_d, 1), (uint32_t)max(max_d, 0), min_cov, rel_threshold,
                    edges, max_edges, selected, counters};
-  uint4 c = make_uint4(0, 0, 0, 0);
+  uint4 c = make_uint4(0xFFFFFFFFu, 0, 0, 0);
   if (i < n_cand) c = cand[i];
-  uint32_t n_cand_d = join_candidate(i < n_cand, c, J);
+  uint32_t n_cand_d = join_candidate(c.x != 0xFFFFFFFFu, c, J);  // a = 0xFFFFFFFF: hole left by cfk_pair_sketch's chunked output
   for (int o = 16; o >= 1; o >>= 1) n_cand_d += __shfl_xor_sync(FULL, n_cand_d, o);
   if ((threadIdx.x & 31) == 0 && n_cand_d) atomicAdd((unsigned long long*)(counters + 2), (unsigned long long)n_cand_d);
 }

@@ -488,7 +488,9 @@ class Engine:
             n_cand = int(c[0])
             if n_cand <= max_cand:
                 break
-            max_cand = n_cand  # exact size is now known: one more pass
+            # the size is now known: one more pass (the sketch kernel hands out the array in per-warp chunks of 256, so
+            # the total moves by a few chunks from run to run: leave room for one chunk per warp)
+            max_cand = n_cand + (self.n_sms * 32 * 256 if use_sketch else 0)
             del cand
         self.cand_hint = max(self.cand_hint, int(n_cand * 1.05) + 1024)
         selected = self._zeros(n_kmers, t.uint8)
@@ -514,7 +516,8 @@ class Engine:
                   self._stream())
         n_sel = int(counters3.cpu()[0])
         return DistResult(edges=edges[: n_edges * 4].view(n_edges, 4), selected=sel_idx[:n_sel],
-                          n_candidates=int(c2[2]), n_pair_candidates=n_cand, n_increments=int(c[2]),
+                          n_candidates=int(c2[2]), n_pair_candidates=int(c[4]) if use_sketch else n_cand,
+                          n_increments=int(c[2]),
                           n_splits=int(c[3]))
 
     # ---- whole path -------------------------------------------------------------------------

@@ -230,7 +230,11 @@ int64_t cfk_sketch_codes_elems(int64_t n_entries, int64_t n_units);
  * NULL keeps the ids' own order.  Pass the same pointer (or NULL) to cfk_pair_sketch. */
 int cfk_sketch_codes(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, uint16_t* codes, uint32_t* perm_ids,
                      cfk_stream_t stream);
-/* occ_last = cfk_occ_last output, or NULL (unit_last[g] is looked up instead). */
+/* occ_last = cfk_occ_last output, or NULL (unit_last[g] is looked up instead).
+ * Output layout: every warp fills its own chunks of 256 candidate slots (one atomic on the cursor per chunk instead
+ * of one per pass); the unused tail of a chunk holds holes, a = 0xFFFFFFFF, which cfk_pair_join skips.  counters[0] is
+ * therefore the number of SLOTS handed out (size cand for it, plus a chunk per warp when retrying), counters[4] the
+ * number of candidates among them. */
 int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t* codes, const uint32_t* perm_ids,
                     const uint32_t* unit_last,
                     const int64_t* occ_ptr, const uint32_t* occ, const uint32_t* occ_last, int64_t n_entries, int64_t n_kmers, int64_t a_begin,
