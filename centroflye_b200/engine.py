@@ -102,7 +102,7 @@ class Engine:
         self.sketch_banked = 1    # stage C sketch: bank-aware placement of the codes (0: the ids' own order)
         self.use_occ_last = 1     # stage C/D read unit_last through a per-occurrence copy (0: chase unit_last[g])
         self.index_cap_mult = 0   # slots per key of the rare-set probe table; 0 = by size (build_index)
-        self.table_load = 0.6  # distinct k-mers <= occurrences, so the stage-A table is at most this full
+        self.table_load = 0.75  # distinct k-mers <= occurrences, so the stage-A table is at most this full (measured: 0.45 / 0.6 / 0.75 -> 26.4 / 26.0 / 25.8 ms per step)
         # stage C kernel: "auto" = sketch where it applies, "exact" = always the exact tables, "sketch" = insist
         self.pair_mode = os.environ.get("CFK_PAIR_MODE", "auto")
         # stage A kernel: "resident" = (read, pass) items with the read staged in shared memory, "tiled" = one block per read
