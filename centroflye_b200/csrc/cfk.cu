@@ -1788,12 +1788,6 @@ __device__ __forceinline__ uint32_t join_candidate(bool active, uint4 c, const J
 // exact tables.  A pass whose set overflows is abandoned before anything is emitted and redone
 // over fewer distances / a narrower id range.
 // ============================================================================================
-#ifndef CFK_SKETCH_ALL_ROWS
-#define CFK_SKETCH_ALL_ROWS 1
-#endif
-#ifndef CFK_SKETCH_CACHED
-#define CFK_SKETCH_CACHED 1 /* per-source occurrence + unit_ptr window kept in registers (sources with <= 32 occurrences) */
-#endif
 constexpr int SK_BITS = CFK_SKETCH_BITS;
 constexpr int SK_TBL_BYTES = 1 << SK_BITS;
 constexpr uint32_t SK_OFF_MASK = 0x3FFFu;          // code bits 0..13: byte offset in the warp's table (hash, or the null byte)
@@ -2074,7 +2068,6 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
     for (;;) {
       // the next window (rest of this unit, else the next unit of the group): its codes fly during this step
       uint32_t np = p + SK_WINDOW, ne = e, ncb = cb + 1u;
-#if CFK_SKETCH_ALL_ROWS
       // branch-free: the next unit's descriptor is fetched whether or not this unit is finished (it is, four steps out
       // of five), so that the bookkeeping shares one basic block with the rows below
       const bool sw = np >= ne;  // warp-uniform
@@ -2087,29 +2080,11 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
       rest = sw ? (rest & (rest - 1u)) : rest;
       uint2 nw = make_uint2(0, 0);
       if (more) nw = __ldg(A.codes + (size_t)ncb * 32u + lane);
-#else
-      bool more = true;
-      if (np >= ne) {
-        if (rest) {
-          src = __ffs(rest) - 1;
-          rest &= rest - 1;
-          np = __shfl_sync(FULL, up, src);
-          ne = __shfl_sync(FULL, ue, src);
-          ncb = __shfl_sync(FULL, ub, src);
-        } else {
-          more = false;
-        }
-      }
-      uint2 nw = make_uint2(0, 0);
-      if (more) nw = __ldg(A.codes + (size_t)ncb * 32u + lane);
-#endif
-      // level 1, one row of 32 entries at a time (rows behind the end of the unit are skipped; padding inside the last
-      // row reads the null byte).  Non-flagged entries of one unit have distinct hashes, so all stores of a step hit
-      // distinct bytes: plain ld/st.
-#if CFK_SKETCH_ALL_ROWS
-      // all four rows, unconditionally: the slots behind the end of a unit hold null codes (they read an always-zero pad
-      // word and do not store), and without the per-row branches the four load / add / store chains are one basic block
-      // that the scheduler interleaves -- with 5.5 warps per scheduler the fixed ALU latencies are the top stall
+      // level 1: four rows of 32 entries.  Non-flagged entries of one unit have distinct hashes, so all stores of a step
+      // hit distinct bytes: plain ld/st.  All four rows run unconditionally -- the slots behind the end of a unit hold
+      // null codes (they read an always-zero pad word and do not store) -- because without per-row branches the four
+      // load / add / store chains are one basic block that the scheduler interleaves: with 5.5 warps per scheduler the
+      // fixed ALU latencies were the top stall (15.96 -> 15.08 ms; skipping the unused rows saved wavefronts, not time)
       const uint32_t a0 = tbase + (w.x & SK_OFF_MASK), a1 = tbase + ((w.x >> 16) & SK_OFF_MASK);
       const uint32_t a2 = tbase + (w.y & SK_OFF_MASK), a3 = tbase + ((w.y >> 16) & SK_OFF_MASK);
       const uint32_t o0 = lds_u8(a0), o1 = lds_u8(a1), o2 = lds_u8(a2), o3 = lds_u8(a3);
@@ -2117,30 +2092,6 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
       if ((int32_t)w.x >= 0) sts_u8(a1, min(o1 + 1u, 255u));
       if (!(w.y & SK_DUP)) sts_u8(a2, min(o2 + 1u, 255u));
       if ((int32_t)w.y >= 0) sts_u8(a3, min(o3 + 1u, 255u));
-#else
-      const uint32_t rem = e - p;
-      uint32_t o0, o1 = 0, o2 = 0, o3 = 0;  // counters before this unit's increment (0 for the rows not run)
-      {
-        const uint32_t a0 = tbase + (w.x & SK_OFF_MASK);
-        o0 = lds_u8(a0);
-        if (!(w.x & SK_DUP)) sts_u8(a0, min(o0 + 1u, 255u));
-      }
-      if (rem > 32u) {
-        const uint32_t a1 = tbase + ((w.x >> 16) & SK_OFF_MASK);
-        o1 = lds_u8(a1);
-        if ((int32_t)w.x >= 0) sts_u8(a1, min(o1 + 1u, 255u));
-        if (rem > 64u) {
-          const uint32_t a2 = tbase + (w.y & SK_OFF_MASK);
-          o2 = lds_u8(a2);
-          if (!(w.y & SK_DUP)) sts_u8(a2, min(o2 + 1u, 255u));
-          if (rem > 96u) {
-            const uint32_t a3 = tbase + ((w.y >> 16) & SK_OFF_MASK);
-            o3 = lds_u8(a3);
-            if ((int32_t)w.y >= 0) sts_u8(a3, min(o3 + 1u, 255u));
-          }
-        }
-      }
-#endif
       // one test for the common case "nothing hot in this step"
       if (__any_sync(FULL, max(max(o0, o1), max(o2, o3)) >= thr)) {
         const bool hs[4] = {o0 >= thr, o1 >= thr, o2 >= thr, o3 >= thr};
@@ -2200,7 +2151,6 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
   const int lane = threadIdx.x & 31;
   int d0 = dmin;
   int nd_force = SK_ND_MAX;
-#if CFK_SKETCH_CACHED
   // Sources with at most 32 occurrences (nearly all: the rare band caps the reads per k-mer): lane t keeps occurrence t
   // -- its unit g_t and the end of its read -- and a sliding window W[i] = unit_ptr[min(g_t + d0 + i, last_t + 1)],
   // i = 0..4, in registers.  Planning a pass (how many distances fit the sketch) and starting it then need no load at
@@ -2225,10 +2175,6 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
       }
     }
   };
-#else
-  const bool cached = false;
-  auto advance_d = [&](int by) { d0 += by; };
-#endif
   while (d0 <= dlim) {
     // plan: extend the pass one distance at a time (4 looked up per round) while the cloud entries fit SK_CAP
     const int nd_max = min(nd_force, dlim - d0 + 1);
@@ -2237,11 +2183,9 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
     bool stop = false;
     for (int jb = 0; jb < nd_max && !stop; jb += 4) {
       uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-#if CFK_SKETCH_CACHED
       if (cached && jb == 0) {
         c0 = W1 - W0; c1 = W2 - W1; c2 = W3 - W2; c3 = W4 - W3;
       } else
-#endif
       for (int64_t t0 = 0; t0 < A.m; t0 += 32) {
         const int64_t t = t0 + lane;
         if (t < A.m) {
@@ -2267,12 +2211,8 @@ __device__ void sketch_source(uint32_t tbase, const SketchArgs& A, int dmin, int
     if (tot == 0) { advance_d(nd); nd_force = SK_ND_MAX; continue; }
     bool redo = false;
     int64_t lo_id = 0, width = A.n_kmers;
-#if CFK_SKETCH_CACHED
     const SketchPre pre{W0, W1, cg + d0};  // W0 == W1 for the lanes without a unit at this distance
     const SketchPre* prep = (cached && nd == 1) ? &pre : nullptr;
-#else
-    const SketchPre* prep = nullptr;
-#endif
     while (lo_id < A.n_kmers) {
       const int64_t hi_id = min(A.n_kmers, lo_id + width);
       const int emitted = sketch_pass(tbase, A, d0, nd, lo_id, hi_id, prep);

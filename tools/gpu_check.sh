@@ -1,4 +1,5 @@
 #!/bin/bash
+# Full GPU test suite, then tools/ab_modes.py $SWITCH (A/B of an engine switch on one input generation).  Outputs -> gpurun_out/
 mkdir -p gpurun_out
 echo "== pytest =="
 timeout -k 10 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/pytest_occ.log
