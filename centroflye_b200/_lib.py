@@ -64,6 +64,9 @@ SIGNATURES = {
     "cfk_ncrf_ids_bytes": (_i64, [_p]),
     "cfk_ncrf_export": (_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "cfk_ncrf_close": (None, [_p]),
+    # native edge file writer (host pointers)
+    "cfk_writer_last_error": (ctypes.c_char_p, []),
+    "cfk_write_edges": (_int, [ctypes.c_char_p, _p, _i64, _i32, _p, _p, _p, _p, _i64, _i32]),
 }
 
 _lib = None

@@ -7,7 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "cfk.cu")
 INGEST_SRC = os.path.join(HERE, "csrc", "ncrf_ingest.cpp")  # host-side NCRF ingestion, same library
-SOURCES = [SRC, INGEST_SRC]
+WRITER_SRC = os.path.join(HERE, "csrc", "result_writer.cpp")  # host-side edge file writer, same library
+SOURCES = [SRC, INGEST_SRC, WRITER_SRC]
 HDR = os.path.join(os.path.dirname(HERE), "include", "cfk.h")
 OUT = os.path.join(HERE, "libcfk.so")
 

@@ -161,8 +161,9 @@ class ShardedRecruiter:
         return CloudCSR(unit_ptr=unit_ptr, ids=ids_all, n_units=n_units, n_entries=int(ids_all.numel())), unit_last
 
     # ---- whole path ---------------------------------------------------------------------------------------
-    def step(self, lo, hi, max_nonuniq, min_d, max_d, min_cov, rel_threshold=0.8, gather=True):
-        """-> (index, local CloudCSR, DistResult); with gather=True every rank ends up with all edges / endpoints."""
+    def step(self, lo, hi, max_nonuniq, min_d, max_d, min_cov, rel_threshold=0.8, gather=True, on_clouds=None):
+        """-> (index, local CloudCSR, DistResult); with gather=True every rank ends up with all edges / endpoints.
+        on_clouds(index, csr) is called as soon as the rare set and this rank's clouds are final."""
         from .engine import DistResult
         eng, t = self.eng, self.torch
         table = eng.count_docfreq(self.reads, self.k)
@@ -171,6 +172,8 @@ class ShardedRecruiter:
         del table
         index = eng.build_index(rare, presorted=True)
         csr = eng.build_clouds(self.reads, self.dunits, self.k, index)
+        if on_clouds is not None:
+            on_clouds(index, csr)
         with eng._stage("gather_clouds"):
             gcsr, unit_last = self.global_clouds(csr)
         res = eng.dist_edges(gcsr, unit_last, index.n, min_d, max_d, min_cov, rel_threshold,
@@ -202,10 +205,20 @@ class ShardedRecruiter:
         eng = self.eng
         self.reads = eng.upload_reads(self.batch, self.k)
         self.dunits = eng.upload_units(self.units, self.k)
-        index, csr, res = self.step(lo, hi, max_nonuniq, min_d, max_d, min_cov, gather=False)
-        want = dict(unit_ptr=csr.unit_ptr, ids=csr.ids, edges=res.edges)
+        early = {}
+
+        def clouds_home(index, csr):  # the clouds (and the rare set) travel while the distance graph is computed
+            want = dict(unit_ptr=csr.unit_ptr, ids=csr.ids)
+            if self.rank == 0:
+                want["rare_keys"] = index.sorted_keys
+            early.update(eng.start_host_copy(**want))
+
+        index, csr, res = self.step(lo, hi, max_nonuniq, min_d, max_d, min_cov, gather=False, on_clouds=clouds_home)
+        want = dict(edges=res.edges)
         if self.rank == 0:
-            want.update(selected=res.selected, rare_keys=index.sorted_keys)
+            want["selected"] = res.selected
         out = eng.to_host(**want)  # pinned result buffers; synchronises
+        eng.finish_host_copies()
+        out.update(early)
         d2h = sum(x.numel() * x.element_size() for x in out.values())
         return self.reads.h2d_bytes + self.dunits.h2d_bytes, d2h

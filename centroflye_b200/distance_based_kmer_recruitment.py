@@ -125,9 +125,11 @@ class KmerRanks(Mapping):
 class EdgeList(Sequence):
     """Edges as the reference's tuples ``(dist, i, j, freq)``, sorted by (dist, i, j), numpy-backed."""
 
-    def __init__(self, dist, i, j, freq):
-        order = np.lexsort((j, i, dist))
-        self.dist, self.i, self.j, self.freq = dist[order], i[order], j[order], freq[order]
+    def __init__(self, dist, i, j, freq, presorted=False):
+        if not presorted:
+            order = np.lexsort((j, i, dist))
+            dist, i, j, freq = dist[order], i[order], j[order], freq[order]
+        self.dist, self.i, self.j, self.freq = (np.ascontiguousarray(x, dtype=np.int64) for x in (dist, i, j, freq))
 
     def __len__(self):
         return int(self.dist.size)
@@ -254,12 +256,27 @@ def filter_dist_tuples(dist_cnt, min_coverage, rel_threshold=0.8):
         raise TypeError("filter_dist_tuples needs the DistCounts handle returned by get_kmer_dist_map "
                         "(the counting and the filter are fused on the device)")
     res = dist_cnt.run(min_coverage, rel_threshold)
-    e = to_host_u32(res.edges).reshape(-1, 4)
+    edges, presorted = _sort_edges_on_device(res.edges, dist_cnt.state.index.n, dist_cnt.max_d)
+    e = to_host_u32(edges).reshape(-1, 4)
     dist_cnt.n_increments = res.n_increments
     selected_kmers = set(to_host_u32(res.selected).tolist())
     selected_edges = EdgeList(e[:, 2].astype(np.int64), e[:, 0].astype(np.int64), e[:, 1].astype(np.int64),
-                              e[:, 3].astype(np.int64))
+                              e[:, 3].astype(np.int64), presorted=presorted)
     return selected_kmers, selected_edges
+
+
+def _sort_edges_on_device(edges, n_kmers, max_d):
+    """Edges (a, b, d, cnt) -> the same rows ordered by (d, a, b), sorted on the device when the three fields fit one
+    63-bit key (they do unless there are more than 2^24 k-mer ids); (edges, False) otherwise (EdgeList sorts on the host)."""
+    n = int(edges.shape[0])
+    id_bits = max(1, int(max(n_kmers - 1, 1)).bit_length())
+    d_bits = max(1, int(max(max_d, 1)).bit_length())
+    if n == 0 or 2 * id_bits + d_bits > 62:
+        return edges, n == 0
+    import torch
+    cols = edges.to(torch.int64) & 0xFFFFFFFF  # uint32 bit patterns
+    key = (cols[:, 2] << (2 * id_bits)) | (cols[:, 0] << id_bits) | cols[:, 1]
+    return edges[torch.argsort(key)], True
 
 
 def output_results(kmer_index, min_coverage, unique_kmers_ind, dist_edges, outdir):
@@ -275,6 +292,9 @@ def output_results(kmer_index, min_coverage, unique_kmers_ind, dist_edges, outdi
         kmers = sorted(kmer_of(sorted(unique_kmers_ind)))
         f.write(''.join(kmer + '\n' for kmer in kmers))
     edges_out_fn = os.path.join(outdir, f'unique_edges_min_edge_cov_{min_coverage}.txt')
+    if isinstance(dist_edges, EdgeList) and isinstance(kmer_index, KmerRanks):
+        write_edges_native(edges_out_fn, kmer_index, dist_edges)
+        return
     with open(edges_out_fn, 'w') as f:
         if isinstance(dist_edges, EdgeList):
             step = 1 << 18
@@ -287,6 +307,19 @@ def output_results(kmer_index, min_coverage, unique_kmers_ind, dist_edges, outdi
             for t in dist_edges:
                 a, b = kmer_of([t[1], t[2]])
                 f.write(f'{t[0]} {a} {b} {t[3]}\n')
+
+
+def write_edges_native(path, kmer_index, dist_edges, threads=0):
+    """The edge file of output_results (dbkr.py:165-171) through libcfk.so's multi-threaded writer (cfk_write_edges);
+    byte-identical to the f-string loop above (tests/test_result_writer.py)."""
+    from . import _lib
+    lib = _lib.load()
+    keys = np.ascontiguousarray(kmer_index.keys_u64, dtype=np.uint64)
+    rc = lib.cfk_write_edges(os.fsencode(path), keys.ctypes.data, int(keys.size), int(kmer_index.k),
+                             dist_edges.dist.ctypes.data, dist_edges.i.ctypes.data, dist_edges.j.ctypes.data,
+                             dist_edges.freq.ctypes.data, len(dist_edges), int(threads))
+    if rc != 0:
+        raise OSError(lib.cfk_writer_last_error().decode(errors="replace"))
 
 
 def main(argv=None):

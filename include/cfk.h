@@ -291,6 +291,15 @@ int cfk_ncrf_export(const cfk_ncrf_t* ctx, uint32_t* packed_h, int64_t* read_off
                     char* ids_h, int64_t* fields_h);
 void cfk_ncrf_close(cfk_ncrf_t* ctx);
 
+/* ---- native result writer (host code) ------------------------------------
+ * Writes the edge file of output_results, distance_based_kmer_recruitment.py:165-171: one line
+ * "{dist} {kmer_i} {kmer_j} {cnt}\n" per edge, k-mers decoded from keys_sorted_h[id] (id = rank in the sorted rare
+ * set), formatted by n_threads host threads (<= 0: all cores) and written in the given order; byte-identical to the
+ * Python writer.  All pointers are HOST pointers; ids outside [0, n_keys) are an error. */
+const char* cfk_writer_last_error(void);
+int cfk_write_edges(const char* path, const uint64_t* keys_sorted_h, int64_t n_keys, int32_t k, const int64_t* dist_h,
+                    const int64_t* i_h, const int64_t* j_h, const int64_t* freq_h, int64_t n_edges, int32_t n_threads);
+
 #ifdef __cplusplus
 }
 #endif
