@@ -99,3 +99,48 @@ def test_native_ingest_errors(tmp_path):
         native_ingest(_write(tmp_path, "r 30 16 0-16 ACGT\n" + f"{MOTIF}+ 16bp score=1 ACGT\n"), min_record_len=0)
     with pytest.raises(FileNotFoundError):
         native_ingest(str(tmp_path / "missing.ncrf"))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_native_ingest_random_reports(tmp_path, seed):
+    """Random small reports: gaps in both rows, both strands, lower-case motif rows, repeated read ids with longer and
+    shorter alignments, comment and blank lines, units cut at the ends -- native ingestion == Python host path."""
+    rng = np.random.default_rng(seed)
+    motif = "".join(rng.choice(list("ACGT"), size=int(rng.integers(5, 40))))
+    lines = ["# random report", ""]
+    ids = [f"read_{i}" for i in range(12)]
+    for rec in range(30):
+        r_id = ids[int(rng.integers(0, len(ids)))]
+        n_units = int(rng.integers(0, 6))
+        cut_l, cut_r = int(rng.integers(0, len(motif))), int(rng.integers(0, len(motif)))
+        truth = (motif * (n_units + 2))[cut_l: len(motif) * (n_units + 2) - cut_r]
+        r_row, m_row = [], []
+        for ch in truth:  # truth alignment with substitutions, insertions and deletions
+            x = rng.random()
+            if x < 0.05:
+                r_row.append(str(rng.choice(list("ACGT")))); m_row.append(ch)
+            elif x < 0.09:
+                r_row.append("-"); m_row.append(ch)
+            elif x < 0.13:
+                r_row.append(str(rng.choice(list("ACGT")))); m_row.append("-")
+                r_row.append(ch); m_row.append(ch)
+            else:
+                r_row.append(ch); m_row.append(ch)
+        r_al, m_al = "".join(r_row), "".join(m_row)
+        if not r_al.replace("-", ""):
+            continue
+        if rng.random() < 0.3:
+            m_al = m_al.lower()
+        strand = "-" if rng.random() < 0.5 else "+"
+        n_bases = len(r_al.replace("-", ""))
+        if strand == "-":
+            r_al, m_al = RC(r_al), RC(m_al)
+        lines.append(f"{r_id} {n_bases + 20} {n_bases}bp 5-{5 + n_bases} {r_al}")
+        lines.append(f"{motif}{strand} {len(m_al.replace('-', ''))}bp score={int(rng.integers(0, 999))} {m_al}")
+        if rng.random() < 0.2:
+            lines.append("# interleaved comment")
+        if rng.random() < 0.2:
+            lines.append("   ")
+    fn = _write(tmp_path, "\n".join(lines) + "\n")
+    for n in (1, 2, 3):
+        _same(fn, n, min_record_len=int(rng.integers(0, 60)), threads=int(rng.integers(0, 3)))

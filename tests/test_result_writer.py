@@ -45,3 +45,25 @@ def test_native_writer_rejects_bad_ids(tmp_path):
     el = dbkr.EdgeList(np.array([1]), np.array([0]), np.array([3]), np.array([4]))
     with pytest.raises(OSError, match="outside"):
         dbkr.write_edges_native(str(tmp_path / "x.txt"), ranks, el)
+
+
+@pytest.mark.parametrize("n_kmers,max_d", [(1000, 150), (1 << 20, 150), (3, 1), ((1 << 28), 1 << 12)])
+def test_device_edge_sort_matches_host_lexsort(n_kmers, max_d):
+    """_sort_edges_on_device (torch; CPU tensors here) orders (a, b, d, cnt) rows by (d, a, b) like EdgeList's lexsort,
+    and declines when the three fields do not fit one key."""
+    import torch
+    rng = np.random.default_rng(n_kmers % 1000 + max_d)
+    n = 5000
+    # distinct (d, a, b) triples, ids up to n_kmers - 1 (uint32 bit patterns in an int32 tensor)
+    trip = np.unique(np.stack([rng.integers(0, n_kmers, n), rng.integers(0, n_kmers, n), rng.integers(1, max_d + 1, n)], 1), axis=0)
+    rng.shuffle(trip)
+    e = np.concatenate([trip, rng.integers(4, 99, (trip.shape[0], 1))], 1).astype(np.uint32)
+    got, presorted = dbkr._sort_edges_on_device(torch.from_numpy(e.view(np.int32)), n_kmers, max_d)
+    fits = 2 * max(1, (n_kmers - 1).bit_length()) + max(1, max_d.bit_length()) <= 62
+    assert presorted == fits
+    got = got.numpy().view(np.uint32)
+    if fits:
+        order = np.lexsort((e[:, 1], e[:, 0], e[:, 2]))
+        assert np.array_equal(got, e[order])
+    else:
+        assert np.array_equal(got, e)
