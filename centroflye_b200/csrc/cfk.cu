@@ -489,6 +489,52 @@ docfreq_resident_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Total-occurrence count: every k-mer occurrence of every read adds 1 -- no per-read
+// de-duplication -- into the same 16-byte-slot table (the n_reads field holds the count, n_multi stays 0).
+// Replaces get_kmer_counts_reads, scripts/better_consensus_unit_reconstruction.py:127-135.
+// One block per tile of KC_TILE consecutive k-mer starts of one read (tile_read / tile_start from the host);
+// a thread rolls 8 consecutive k-mers out of three packed words.
+// --------------------------------------------------------------------------------------------
+constexpr int KC_THREADS = 256;
+constexpr int KC_PER_THREAD = 8;
+constexpr int KC_TILE = KC_THREADS * KC_PER_THREAD;
+
+__global__ void __launch_bounds__(KC_THREADS)
+kmer_count_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ read_off, const int64_t* __restrict__ read_len,
+                  const int32_t* __restrict__ tile_read, const int64_t* __restrict__ tile_start, int k, uint64_t* table,
+                  int64_t cap, int64_t* counters) {
+  const int64_t r = tile_read[blockIdx.x];
+  const int64_t nk = read_len[r] - k + 1;
+  const int64_t base = tile_start[blockIdx.x] + (int64_t)threadIdx.x * KC_PER_THREAD;
+  if (base >= nk) return;
+  const uint32_t* words = packed + (read_off[r] >> 4);  // every read starts on a 64-base boundary
+  const uint64_t mask = (1ull << (2 * k)) - 1;
+  const int npos = (int)min((int64_t)KC_PER_THREAD, nk - base);
+  // 48-base window from the word of `base` (a multiple of 8): offset + 7 + k - 1 <= 8 + 7 + 30 < 48
+  const int64_t w0 = base >> 4;
+  uint64_t win_lo = (uint64_t)__ldg(words + w0) | ((uint64_t)__ldg(words + w0 + 1) << 32);
+  uint32_t win_hi = __ldg(words + w0 + 2);
+  if (base & 8) {
+    win_lo = (win_lo >> 16) | ((uint64_t)win_hi << 48);
+    win_hi >>= 16;
+  }
+  uint64_t kmer = 0;
+  for (int i = 0; i < k - 1; ++i) {
+    kmer = (kmer << 2) | (win_lo & 3u);
+    win_lo = (win_lo >> 2) | ((uint64_t)win_hi << 62);
+    win_hi >>= 2;
+  }
+  for (int j = 0; j < npos; ++j) {
+    kmer = ((kmer << 2) | (win_lo & 3u)) & mask;
+    win_lo = (win_lo >> 2) | ((uint64_t)win_hi << 62);
+    win_hi >>= 2;
+    const int64_t slot = slot_upsert(table, cap, kmer, home_slot(mix64(kmer), cap));
+    if (slot < 0) counters[0] = 1;
+    else atomicAdd(reinterpret_cast<uint32_t*>(table + 2 * slot + 1), 1u);
+  }
+}
+
 __global__ void table_init_kernel(uint64_t* table, int64_t cap) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cap) reinterpret_cast<ulonglong2*>(table)[i] = make_ulonglong2(EMPTY, 0ull);
@@ -2370,6 +2416,20 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
   CFK_CHECK_LAUNCH("docfreq_resident_kernel", 1);
   return CFK_OK;
 }
+
+int cfk_kmer_count_total(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* tile_read,
+                         const int64_t* tile_start, int64_t n_tiles, int k, uint64_t* table, int64_t cap, int64_t* counters,
+                         cfk_stream_t stream) {
+  if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_kmer_count_total: k must be in [1, 31]");
+  if (cap < 1 || n_tiles < 0 || n_tiles >= (1ll << 31)) return fail(CFK_ERR_INVALID, "cfk_kmer_count_total: bad sizes");
+  if (n_tiles == 0) return CFK_OK;
+  kmer_count_kernel<<<(unsigned)n_tiles, KC_THREADS, 0, (cudaStream_t)stream>>>(packed, read_off, read_len, tile_read, tile_start, k,
+                                                                              table, cap, counters);
+  CFK_CHECK_LAUNCH("kmer_count_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_kmer_count_tile(void) { return KC_TILE; }
 
 int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n, uint64_t* table,
                     int64_t cap, int64_t* counters, cfk_stream_t stream) {

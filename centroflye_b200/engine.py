@@ -281,6 +281,28 @@ class Engine:
                 return table
             cap *= 2
 
+    def count_total(self, reads, batch, k):
+        """Total occurrences of every k-mer over all reads (no per-read de-duplication) -> DocFreqTable whose n_reads
+        field holds the count (better_consensus_unit_reconstruction.py:127-135)."""
+        k = check_k(k)
+        tile = int(self.lib.cfk_kmer_count_tile())
+        nk = np.maximum(batch.read_len - k + 1, 0)
+        tiles_per_read = (nk + tile - 1) // tile
+        tile_read = np.repeat(np.arange(batch.n_reads, dtype=np.int32), tiles_per_read)
+        first = np.cumsum(tiles_per_read) - tiles_per_read
+        tile_start = (np.arange(tile_read.size, dtype=np.int64) - np.repeat(first, tiles_per_read)) * tile
+        d_read, d_start = self._to_dev(tile_read), self._to_dev(tile_start)
+        cap = max(1024, int(int(nk.sum()) / self.table_load) + 1)
+        while True:
+            table = self.new_table(cap)
+            counters = self._counters()
+            _lib.call("cfk_kmer_count_total", self._p(reads.packed), self._p(reads.read_off), self._p(reads.read_len),
+                      self._p(d_read), self._p(d_start), int(tile_read.size), k, self._p(table.slots), cap,
+                      self._p(counters), self._stream())
+            if int(counters.cpu()[0]) == 0:
+                return table
+            cap *= 2
+
     def table_select(self, table, lo, hi, max_nonuniq, with_counts=False, n_parts=0, part=0):
         """Compacted (keys[, n_reads, n_multi]) of slots inside the band, unordered."""
         t = self.torch

@@ -96,6 +96,16 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
                                const int32_t* order, const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* table,
                                int64_t cap, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
 
+/* Total-occurrence count: replaces get_kmer_counts_reads,
+ * scripts/better_consensus_unit_reconstruction.py:127-135 -- every k-mer occurrence of every gap-free read row adds 1
+ * (no per-read de-duplication).  Same table as cfk_docfreq_count; the count lands in the n_reads field, n_multi stays
+ * 0.  The k-mer starts of the reads are cut into tiles of cfk_kmer_count_tile() positions: tile_read[t] = read of
+ * tile t, tile_start[t] = its first k-mer start inside that read.  counters[0] != 0: table full. */
+int cfk_kmer_count_tile(void);
+int cfk_kmer_count_total(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* tile_read,
+                         const int64_t* tile_start, int64_t n_tiles, int k, uint64_t* table, int64_t cap, int64_t* counters,
+                         cfk_stream_t stream);
+
 /* Merge (key, n_reads, n_multi) records counted elsewhere (another GPU's shard) into a table:
  * the owner-side half of the multi-GPU all-to-all.  counters[0] != 0: full. */
 int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n, uint64_t* table,

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import all_case_points, clouds_to_csr
+from conftest import all_case_points, clouds_to_csr, golden_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -237,3 +237,22 @@ def test_sharded_recruitment_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "multi-gpu ok" in out.stdout
+
+
+@pytest.mark.parametrize("case", golden_cases())
+@pytest.mark.parametrize("k", [19, 30])
+def test_total_kmer_counts_match_reference_loop(golden, mods, case, k):
+    """get_kmer_counts_reads (better_consensus_unit_reconstruction.py:127-135, restated: every k-mer occurrence of every
+    gap-free read row counts) on the device."""
+    from collections import Counter
+    from centroflye_b200.better_consensus_unit_reconstruction import get_kmer_counts_reads
+    _, _, NCRF_Report = mods
+    rep = NCRF_Report(golden(case).report_path)
+    want = Counter()
+    for rec in rep.records.values():
+        s = rec.r_al.replace("-", "")
+        want.update(s[i:i + k] for i in range(len(s) - k + 1))
+    got = get_kmer_counts_reads(rep, k=k)
+    assert len(got) == len(want)
+    assert dict(got.items()) == dict(want)
+    assert got["A" * k] == want.get("A" * k, 0) and got["not a kmer"] == 0
