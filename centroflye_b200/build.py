@@ -8,7 +8,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "cfk.cu")
 INGEST_SRC = os.path.join(HERE, "csrc", "ncrf_ingest.cpp")  # host-side NCRF ingestion, same library
 WRITER_SRC = os.path.join(HERE, "csrc", "result_writer.cpp")  # host-side edge file writer, same library
-SOURCES = [SRC, INGEST_SRC, WRITER_SRC]
+STREAM_SRC = os.path.join(HERE, "csrc", "docfreq_stream.cu")  # stage A, two-phase form (emit + apply)
+COMMON_HDR = os.path.join(HERE, "csrc", "cfk_common.cuh")
+SOURCES = [SRC, STREAM_SRC, INGEST_SRC, WRITER_SRC]
 HDR = os.path.join(os.path.dirname(HERE), "include", "cfk.h")
 OUT = os.path.join(HERE, "libcfk.so")
 
@@ -24,7 +26,7 @@ def nvcc_path():
 
 
 def up_to_date():
-    return os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(HDR), *(os.path.getmtime(p) for p in SOURCES))
+    return os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(HDR), os.path.getmtime(COMMON_HDR), *(os.path.getmtime(p) for p in SOURCES))
 
 
 def build(force=False, verbose=False):

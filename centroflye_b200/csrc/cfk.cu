@@ -6,50 +6,22 @@
 //
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo
 //             -shared -Xcompiler -fPIC -o libcfk.so cfk.cu
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
-#include "../../include/cfk.h"
+#include "cfk_common.cuh"
+
+thread_local char cfk_g_err[512] = "";
+long long cfk_g_launches = 0;  // kernels enqueued through this library (bench.py reports it)
 
 namespace {
 
-constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr uint64_t EMPTY = CFK_EMPTY_KEY;
-
-thread_local char g_err[512] = "";
-long long g_launches = 0;  // kernels enqueued through this library (bench.py reports it)
-
-int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
-  if (e != cudaSuccess)
-    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
-  else
-    snprintf(g_err, sizeof(g_err), "%s", what);
-  return code;
-}
-
-#define CFK_CHECK_LAUNCH(name, n_launched)                        \
-  do {                                                           \
-    cudaError_t e_ = cudaGetLastError();                         \
-    if (e_ != cudaSuccess) return fail(CFK_ERR_CUDA, name, e_);  \
-    __atomic_fetch_add(&g_launches, (long long)(n_launched), __ATOMIC_RELAXED); \
-  } while (0)
-
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
-  x ^= x >> 33;
-  x *= 0xff51afd7ed558ccdULL;
-  x ^= x >> 33;
-  x *= 0xc4ceb9fe1a85ec53ULL;
-  x ^= x >> 33;
-  return x;
-}
-
-// home slot of a hashed key in a table of arbitrary capacity (multiply-shift range reduction)
-__device__ __forceinline__ int64_t home_slot(uint64_t h, int64_t cap) {
-  return (int64_t)__umul64hi(h, (uint64_t)cap);
-}
+using cfk::EMPTY;
+using cfk::FULL;
+using cfk::blocks_for;
+using cfk::fail;
+using cfk::home_slot;
+using cfk::mix64;
 
 __device__ __forceinline__ uint32_t base_at(const uint32_t* __restrict__ packed, int64_t pos) {
   return (__ldg(packed + (pos >> 4)) >> ((pos & 15) << 1)) & 3u;
@@ -2347,7 +2319,6 @@ __global__ void flag_indices_kernel(const uint8_t* __restrict__ flags, int64_t n
   if (take) out[pos] = (uint32_t)i;
 }
 
-inline int64_t blocks_for(int64_t n, int threads) { return (n + threads - 1) / threads; }
 
 }  // namespace
 
@@ -2357,10 +2328,10 @@ inline int64_t blocks_for(int64_t n, int threads) { return (n + threads - 1) / t
 extern "C" {
 
 int cfk_abi_version(void) { return 1; }
-const char* cfk_last_error(void) { return g_err; }
+const char* cfk_last_error(void) { return cfk_g_err; }
 int cfk_pair_table_bytes_per_warp(void) { return PC_TBL_BYTES; }
 int cfk_pair_warps_per_block(void) { return PC_WARPS; }
-int64_t cfk_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+int64_t cfk_launch_count(void) { return (int64_t)__atomic_load_n(&cfk_g_launches, __ATOMIC_RELAXED); }
 
 int cfk_table_init(uint64_t* table, int64_t cap, cfk_stream_t stream) {
   if (cap < 1) return fail(CFK_ERR_INVALID, "cfk_table_init: cap < 1");
@@ -2375,12 +2346,11 @@ int cfk_docfreq_count(const uint32_t* packed, const int64_t* read_off, const int
   if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_docfreq_count: k must be in [1, 31]");
   if (cap < 1 || n_reads < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_docfreq_count: bad sizes");
   if (n_reads == 0) return CFK_OK;
-  static bool attr_done = false;
+  static unsigned long long attr_done = 0;  // per device (bit = device ordinal)
   const int smem = (DF_SET_SLOTS + DF_TILE_WORDS) * 4;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(docfreq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  {
+    cudaError_t e = cfk::ensure_dynamic_smem(docfreq_kernel, smem, &attr_done);
     if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_docfreq_count: cudaFuncSetAttribute", e);
-    attr_done = true;
   }
   docfreq_kernel<<<(unsigned)n_blocks, DF_THREADS, smem, (cudaStream_t)stream>>>(packed, read_off, read_len, order, n_reads,
                                                                                k, table, cap, counters);
@@ -2404,12 +2374,11 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
   if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_docfreq_count_resident: k must be in [1, 31]");
   if (cap < 1 || n_reads < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_docfreq_count_resident: bad sizes");
   if (n_reads == 0) return CFK_OK;
-  static bool attr_done = false;
+  static unsigned long long attr_done = 0;  // per device (bit = device ordinal)
   const int smem = DF3_SMEM_WORDS * 4;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(docfreq_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  {
+    cudaError_t e = cfk::ensure_dynamic_smem(docfreq_resident_kernel, smem, &attr_done);
     if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_docfreq_count_resident: cudaFuncSetAttribute", e);
-    attr_done = true;
   }
   docfreq_resident_kernel<<<(unsigned)n_blocks * DF3_BLOCKS_PER_SM, DF3_THREADS, smem, (cudaStream_t)stream>>>(
       packed, read_off, read_len, order, item_ptr, n_reads, k, table, cap, counters);
@@ -2641,12 +2610,11 @@ int cfk_pair_candidates(const int64_t* unit_ptr, const uint32_t* ids, const uint
   if (a_begin < 0 || a_end > n_kmers || a_stride < 1) return fail(CFK_ERR_INVALID, "cfk_pair_candidates: bad id range");
   if (max_cand < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_pair_candidates: bad sizes");
   if (a_begin >= a_end || max_d < (min_d > 1 ? min_d : 1)) return CFK_OK;
-  static bool attr_done = false;
+  static unsigned long long attr_done = 0;  // per device (bit = device ordinal)
   const int smem = PC_WARPS * PC_TBL_BYTES;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pair_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  {
+    cudaError_t e = cfk::ensure_dynamic_smem(pair_candidates_kernel, smem, &attr_done);
     if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_pair_candidates: cudaFuncSetAttribute", e);
-    attr_done = true;
   }
   pair_candidates_kernel<<<(unsigned)n_blocks, PC_WARPS * 32, smem, (cudaStream_t)stream>>>(
       unit_ptr, ids, unit_last, occ_ptr, occ, usplit, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov,
@@ -2695,12 +2663,11 @@ int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t
   if (a_begin < 0 || a_end > n_kmers || a_stride < 1) return fail(CFK_ERR_INVALID, "cfk_pair_sketch: bad id range");
   if (max_cand < 0 || n_blocks < 1) return fail(CFK_ERR_INVALID, "cfk_pair_sketch: bad sizes");
   if (a_begin >= a_end || max_d < (min_d > 1 ? min_d : 1)) return CFK_OK;
-  static bool attr_done = false;
+  static unsigned long long attr_done = 0;  // per device (bit = device ordinal)
   const int smem = SK_WARPS * SK_WARP_BYTES;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(pair_sketch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  {
+    cudaError_t e = cfk::ensure_dynamic_smem(pair_sketch_kernel, smem, &attr_done);
     if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_pair_sketch: cudaFuncSetAttribute", e);
-    attr_done = true;
   }
   pair_sketch_kernel<<<(unsigned)n_blocks, SK_WARPS * 32, smem, (cudaStream_t)stream>>>(
       unit_ptr, ids, (const uint2*)codes, perm_ids, unit_last, occ_ptr, occ, occ_last, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,

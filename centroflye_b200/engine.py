@@ -41,6 +41,7 @@ class DeviceReads:
     n_reads: int
     n_bases: int
     h2d_bytes: int
+    max_len: int = 0    # longest read (bases)
 
 
 @dataclass
@@ -105,10 +106,12 @@ class Engine:
         self.table_load = 0.75  # distinct k-mers <= occurrences, so the stage-A table is at most this full (measured: 0.45 / 0.6 / 0.75 -> 26.4 / 26.0 / 25.8 ms per step)
         # stage C kernel: "auto" = sketch where it applies, "exact" = always the exact tables, "sketch" = insist
         self.pair_mode = os.environ.get("CFK_PAIR_MODE", "auto")
-        # stage A kernel: "resident" = (read, pass) items with the read staged in shared memory, "tiled" = one block per read
+        # stage A kernel: "stream" = two-phase (emit hash-partitioned records, apply them partition by partition),
+        # "resident" = (read, pass) items updating the table directly, "tiled" = one block per read
         self.docfreq_mode = os.environ.get("CFK_DOCFREQ_MODE", "resident")
-        if self.docfreq_mode not in ("resident", "tiled"):
-            raise CfkError(f"CFK_DOCFREQ_MODE must be resident or tiled, got {self.docfreq_mode!r}")
+        if self.docfreq_mode not in ("stream", "resident", "tiled"):
+            raise CfkError(f"CFK_DOCFREQ_MODE must be stream, resident or tiled, got {self.docfreq_mode!r}")
+        self.part_slack = 1.25  # records per partition buffer / expected records per partition (stream mode)
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
         self._host_pool = {}  # name -> pinned uint8 buffer for results (to_host)
         self._copy_stream = None  # side stream of start_host_copy
@@ -229,7 +232,8 @@ class Engine:
         return DeviceReads(packed=self._staged(batch, "packed", batch.packed),
                            read_off=self._staged(batch, "read_off", batch.read_off),
                            read_len=self._staged(batch, "read_len", batch.read_len), order=self._to_dev(order),
-                           n_reads=batch.n_reads, n_bases=batch.n_bases, h2d_bytes=h2d)
+                           n_reads=batch.n_reads, n_bases=batch.n_bases, h2d_bytes=h2d,
+                           max_len=int(batch.read_len.max()) if batch.n_reads else 0)
 
     def upload_units(self, units, k):
         nk = np.maximum(units.unit_len.astype(np.int64) - k + 1, 0)
@@ -256,8 +260,12 @@ class Engine:
         k = check_k(k)
         total_k = n_kmers_hint if n_kmers_hint is not None else max(reads.n_bases - reads.n_reads * (k - 1), 0)
         cap = max(1024, int(total_k / self.table_load) + 1)
+        if self.docfreq_mode == "stream" and reads.n_reads:
+            table = self._count_docfreq_stream(reads, k, total_k, cap)
+            if table is not None:
+                return table
         item_ptr = None
-        if self.docfreq_mode == "resident" and reads.n_reads:
+        if self.docfreq_mode in ("resident", "stream") and reads.n_reads:
             n_pass = self._empty(reads.n_reads, self.torch.int32)
             _lib.call("cfk_docfreq_plan", self._p(reads.read_len), self._p(reads.order), reads.n_reads, k,
                       self._p(n_pass), self._stream())
@@ -280,6 +288,43 @@ class Engine:
             if int(c[0]) == 0:
                 return table
             cap *= 2
+
+    def _count_docfreq_stream(self, reads, k, total_k, cap):
+        """Two-phase stage A: cfk_docfreq_emit (per-read sets in shared memory -> hash-partitioned records) and
+        cfk_docfreq_apply (records -> table, one L2-sized window of the table at a time).  Returns None when a
+        partition buffer overflowed (pathological hash skew): the caller falls back to the direct kernel."""
+        t = self.torch
+        if reads.max_len >= (1 << 30):
+            return None  # the set's slots hold a 30-bit position
+        n_parts = int(self.lib.cfk_docfreq_parts())
+        n_pass = self._empty(reads.n_reads, t.int32)
+        _lib.call("cfk_docfreq_emit_plan", self._p(reads.read_len), self._p(reads.order), reads.n_reads, k,
+                  self._p(n_pass), self._stream())
+        item_ptr = self.exclusive_scan(n_pass[:reads.n_reads])
+        # records <= k-mer occurrences; the hash spreads them evenly (heavy k-mers: 2 records per read at most)
+        part_cap = min(int(total_k), int(total_k / n_parts * self.part_slack) + 4096) + 1
+        records = self._empty(n_parts * part_cap, t.int64)
+        cursors = self._zeros(n_parts, t.int64)
+        while True:
+            counters = self._counters()
+            with self._stage("docfreq_emit"):
+                _lib.call("cfk_docfreq_emit", self._p(reads.packed), self._p(reads.read_off), self._p(reads.read_len),
+                          self._p(reads.order), self._p(item_ptr), reads.n_reads, k, self._p(records), part_cap,
+                          self._p(cursors), self._p(counters), self.n_sms, self._stream())
+            table = self.new_table(cap)
+            with self._stage("docfreq_apply"):
+                _lib.call("cfk_docfreq_apply", self._p(records), part_cap, self._p(cursors), k, self._p(table.slots), cap,
+                          self._p(counters), self.n_sms, self._stream())
+            c = counters.cpu()
+            if int(c[1]):
+                raise CfkError("stage A: per-read k-mer set overflowed (internal error)")
+            if int(c[0]) == 0:
+                self.last_docfreq_records = int(cursors.sum().item()) if self.events is not None else None
+                return table
+            if bool((cursors > part_cap).any().item()):
+                return None  # a partition buffer was too small: direct kernel
+            cap *= 2  # the table was: recount into a bigger one (the records are still valid, but keep it simple)
+            cursors.zero_()
 
     def count_total(self, reads, batch, k):
         """Total occurrences of every k-mer over all reads (no per-read de-duplication) -> DocFreqTable whose n_reads

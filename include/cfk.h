@@ -36,6 +36,9 @@ extern "C" {
 
 #define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define CFK_DOCFREQ_SET_SLOTS 49152 /* 32-bit slots of the per-read k-mer set in shared memory (192 KB) */
+#ifndef CFK_DOCFREQ_PART_BITS
+#define CFK_DOCFREQ_PART_BITS 7    /* log2 of the hash partitions of the two-phase stage A (cfk_docfreq_emit / _apply) */
+#endif
 #ifndef CFK_PAIR_WARPS
 #define CFK_PAIR_WARPS 20         /* warps per block of the stage-C kernel (one block per SM) */
 #endif
@@ -95,6 +98,29 @@ int cfk_docfreq_plan(const int64_t* read_len, const int32_t* order, int64_t n_re
 int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len,
                                const int32_t* order, const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* table,
                                int64_t cap, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
+
+/* Two-phase form of stage A (the default path; same table, same results as cfk_docfreq_count).
+ * Replaces get_kmer_freqs_from_ncrf_report, distance_based_kmer_recruitment.py:39-63, in two kernels:
+ *   cfk_docfreq_emit   per (read, pass) item the per-read de-duplication of :50-53 runs in shared memory (the read
+ *                      arrives by one cp.async.bulk copy; the set is built without atomics: claim, barrier, verify)
+ *                      and ONE 8-byte record per distinct k-mer of the read -- bits 0..2k-1 the k-mer, bit 63 set if
+ *                      the k-mer occurs in the read more than once (:55-56) -- is appended to hash partition
+ *                      p = mix64(kmer) >> (64 - CFK_DOCFREQ_PART_BITS): records[p * part_cap + i], i < cursors[p].
+ *   cfk_docfreq_apply  adds the records to the table partition by partition (n_reads += 1, n_multi += bit 63,
+ *                      :57-62 in closed form); the home slot is monotone in the same hash, so a partition's updates
+ *                      stay inside one 1/2^CFK_DOCFREQ_PART_BITS window of the table, i.e. in L2.
+ * cfk_docfreq_emit_plan writes n_pass[i] = passes of read order[i] (-> item_ptr by cfk_exclusive_scan).
+ * cursors[cfk_docfreq_parts()] and counters[8] are zeroed by the caller.  counters: [0] != 0 a partition buffer
+ * (emit) or the table (apply) overflowed -- results invalid, the caller grows / falls back; [1] != 0 internal set
+ * overflow; [2], [3] work tickets. */
+int cfk_docfreq_parts(void);
+int cfk_docfreq_emit_plan(const int64_t* read_len, const int32_t* order, int64_t n_reads, int k, int32_t* n_pass,
+                          cfk_stream_t stream);
+int cfk_docfreq_emit(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* order,
+                     const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* records, int64_t part_cap,
+                     int64_t* cursors, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
+int cfk_docfreq_apply(const uint64_t* records, int64_t part_cap, const int64_t* cursors, int k, uint64_t* table, int64_t cap,
+                      int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
 
 /* Total-occurrence count: replaces get_kmer_counts_reads,
  * scripts/better_consensus_unit_reconstruction.py:127-135 -- every k-mer occurrence of every gap-free read row adds 1

@@ -250,9 +250,10 @@ def test_table_partition_matches_owner_rule(eng):
         assert np.array_equal(m_.cpu().numpy().view(np.uint32)[order], nm)
 
 
-@pytest.fixture(params=["resident", "tiled"])
+@pytest.fixture(params=["stream", "resident", "tiled"])
 def docfreq_mode(eng, request):
-    """Both stage-A kernels: (read, pass) items with the read resident in shared memory, and one block per read."""
+    """The stage-A kernels: two-phase (emit records per read, apply them per hash partition), (read, pass) items
+    updating the table directly, and one block per read."""
     old, eng.docfreq_mode = eng.docfreq_mode, request.param
     yield request.param
     eng.docfreq_mode = old
@@ -277,6 +278,39 @@ def test_docfreq_read_shapes(eng, docfreq_mode, k):
     lens = [0, k - 1, k, k + 1, 63, 64, 65, 1000, 8191, 8192, 8200, 29000, 31000, 70001, 131072, 300000, 700000, 5000, 5000]
     codes = [_repetitive_read(rng, max(n, 0), int(rng.integers(20, 400)), 0.02) for n in lens]
     codes[-1] = codes[-2].copy()  # the same read twice: n_reads 2, n_multi per read as before
+    batch = pack_reads(codes, [f"r{i}" for i in range(len(codes))])
+    table = eng.count_docfreq(eng.upload_reads(batch, k), k)
+    keys, nr, nm = eng.table_select(table, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)
+    keys = keys.cpu().numpy().view(np.uint64)
+    order = np.argsort(keys)
+    wk, wr, wm = c_oracle.docfreq(c_oracle.unpacked_codes(batch), batch, k)
+    assert np.array_equal(keys[order], wk)
+    assert np.array_equal(nr.cpu().numpy().view(np.uint32)[order], wr)
+    assert np.array_equal(nm.cpu().numpy().view(np.uint32)[order], wm)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_docfreq_claim_races(eng, docfreq_mode, seed):
+    """The atomics-free per-read set of the two-phase kernel resolves racing claims in its verify phase.  Reads made
+    to provoke them: tiny alphabets / short periods (a few distinct k-mers hit by thousands of positions at once),
+    many exact copies of one segment at varying offsets, and random reads in between -- against the C restatement of
+    dbkr.py:39-63 at a k where nearly every position of the periodic reads is a duplicate."""
+    from centroflye_b200.ingest import pack_reads
+    from oracle import c_oracle
+    rng = np.random.default_rng(seed)
+    k = [7, 11, 19][seed - 1]
+    codes = []
+    for period in (1, 2, 3, 5, 17, 64, 171):
+        unit = rng.integers(0, 4, size=period, dtype=np.uint8)
+        for n in (5000, 40000, 90000):
+            codes.append(np.tile(unit, n // period + 1)[:n].copy())
+    seg = rng.integers(0, 4, size=3000, dtype=np.uint8)
+    for _ in range(40):
+        parts = [seg if rng.random() < 0.7 else rng.integers(0, 4, size=int(rng.integers(10, 4000)), dtype=np.uint8)
+                 for _ in range(int(rng.integers(2, 30)))]
+        codes.append(np.concatenate(parts))
+    for _ in range(60):
+        codes.append(_repetitive_read(rng, int(rng.integers(5000, 120000)), int(rng.integers(150, 2100)), 0.06))
     batch = pack_reads(codes, [f"r{i}" for i in range(len(codes))])
     table = eng.count_docfreq(eng.upload_reads(batch, k), k)
     keys, nr, nm = eng.table_select(table, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)

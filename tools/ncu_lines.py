@@ -20,24 +20,26 @@ def sass_lines(so_path, kernel):
     with tempfile.TemporaryDirectory() as tmp:
         subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so_path)], cwd=tmp, check=True,
                        capture_output=True)
-        cubin = max((f for f in os.listdir(tmp) if f.endswith(".cubin")), key=lambda f: os.path.getsize(os.path.join(tmp, f)))
-        text = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True,
-                              text=True).stdout
-    out, inside, cur = [], False, None
+        text = ""  # one cubin per translation unit: the kernel lives in one of them
+        for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+            text += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True,
+                                   text=True).stdout
+    out, inside, cur, src_file = [], False, None, None
     for ln in text.splitlines():
         if ln.startswith("//--------------------- .text."):
             inside = kernel in ln
             continue
         if not inside:
             continue
-        m = re.search(r'//## File ".*?", line (\d+)(.*)', ln)
+        m = re.search(r'//## File "(.*?)", line (\d+)(.*)', ln)
         if m:
-            chain = re.findall(r'line (\d+)', m.group(2))
-            cur = (int(m.group(1)), tuple(int(c) for c in chain))
+            chain = re.findall(r'line (\d+)', m.group(3))
+            cur = (int(m.group(2)), tuple(int(c) for c in chain))
+            src_file = src_file or m.group(1)
             continue
         if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
             out.append(cur)
-    return out
+    return out, src_file
 
 
 def main():
@@ -56,7 +58,7 @@ def main():
         # several launches matched: keep the first
         n_first = next((i for i, r in enumerate(rows[hdr + 1:]) if r and r[0] == "Kernel Name"), len(body))
         body = body[:n_first]
-    lines = sass_lines(so, kernel)
+    lines, src_file = sass_lines(so, kernel)
     if len(lines) != len(body):
         print(f"# warning: {len(body)} profiled instructions vs {len(lines)} in the cubin (rebuilt since?)")
     agg = collections.defaultdict(lambda: [0, 0, 0, 0])
@@ -67,7 +69,8 @@ def main():
         for j, v in enumerate(vals):
             agg[key][j] += v
             tot[j] += v
-    src = open(os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", "cfk.cu")).read().splitlines()
+    src_path = os.path.join(os.path.dirname(os.path.abspath(so)), "csrc", os.path.basename(src_file or "cfk.cu"))
+    src = open(src_path).read().splitlines()
     print(f"# {kernel}: {tot[0]:.3e} warp-instructions, {tot[1]:.3e} thread-instructions, {tot[2]} samples, "
           f"{tot[3]:.3e} shared wavefronts")
     print(f"# {'line':>5} {'inst%':>6} {'smp%':>6} {'thr/inst':>8} {'smem wf%':>8}  source")
