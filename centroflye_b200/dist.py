@@ -166,7 +166,7 @@ class ShardedRecruiter:
         on_clouds(index, csr) is called as soon as the rare set and this rank's clouds are final."""
         from .engine import DistResult
         eng, t = self.eng, self.torch
-        table = eng.count_docfreq(self.reads, self.k)
+        table = eng._count_docfreq_direct(self.reads, self.k)  # hashed table: the exchange looks keys up
         with eng._stage("exchange_docfreq"):
             rare = self.global_rare_keys(table, lo, hi, max_nonuniq)
         del table

@@ -59,6 +59,7 @@ class DeviceUnits:
 class DocFreqTable:
     slots: object       # int64[2 * cap]: per slot (key as uint64 bits, -1 = empty ; n_reads | n_multi << 32)
     cap: int
+    dense: bool = False  # True: every slot is occupied and in no particular order (two-phase stage A): scans only
 
 
 @dataclass
@@ -108,7 +109,7 @@ class Engine:
         self.pair_mode = os.environ.get("CFK_PAIR_MODE", "auto")
         # stage A kernel: "stream" = two-phase (emit hash-partitioned records, apply them partition by partition),
         # "resident" = (read, pass) items updating the table directly, "tiled" = one block per read
-        self.docfreq_mode = os.environ.get("CFK_DOCFREQ_MODE", "resident")
+        self.docfreq_mode = os.environ.get("CFK_DOCFREQ_MODE", "stream")
         if self.docfreq_mode not in ("stream", "resident", "tiled"):
             raise CfkError(f"CFK_DOCFREQ_MODE must be stream, resident or tiled, got {self.docfreq_mode!r}")
         self.part_slack = 1.25  # records per partition buffer / expected records per partition (stream mode)
@@ -256,16 +257,32 @@ class Engine:
         return DocFreqTable(slots=slots, cap=int(cap))
 
     def count_docfreq(self, reads, k, n_kmers_hint=None):
-        """One pass over all reads -> DocFreqTable (grown and recounted if the table fills up)."""
+        """One pass over all reads -> DocFreqTable (every distinct k-mer with n_reads and n_multi)."""
         k = check_k(k)
+        if self.docfreq_mode == "stream" and reads.n_reads:
+            out = self.docfreq_stream(reads, k, want_table=True)
+            if out is not None:
+                return out[1]
+        return self._count_docfreq_direct(reads, k, n_kmers_hint)
+
+    def rare_kmers(self, reads, k, lo, hi, max_nonuniq):
+        """Stage A + the band of get_rare_kmers in one go -> unordered rare keys (int64 tensor of uint64 bits)."""
+        k = check_k(k)
+        if lo > hi or max_nonuniq < 0:
+            return self._empty(0, self.torch.int64)[:0]
+        if self.docfreq_mode == "stream" and reads.n_reads:
+            out = self.docfreq_stream(reads, k, band=(lo, hi, max_nonuniq))
+            if out is not None:
+                return out[0]
+        table = self._count_docfreq_direct(reads, k, None)
+        return self.table_select(table, lo, hi, max_nonuniq)
+
+    def _count_docfreq_direct(self, reads, k, n_kmers_hint=None):
+        """The single-kernel forms of stage A (global hash table): "resident" (default of this path) or "tiled"."""
         total_k = n_kmers_hint if n_kmers_hint is not None else max(reads.n_bases - reads.n_reads * (k - 1), 0)
         cap = max(1024, int(total_k / self.table_load) + 1)
-        if self.docfreq_mode == "stream" and reads.n_reads:
-            table = self._count_docfreq_stream(reads, k, total_k, cap)
-            if table is not None:
-                return table
         item_ptr = None
-        if self.docfreq_mode in ("resident", "stream") and reads.n_reads:
+        if self.docfreq_mode != "tiled" and reads.n_reads:
             n_pass = self._empty(reads.n_reads, self.torch.int32)
             _lib.call("cfk_docfreq_plan", self._p(reads.read_len), self._p(reads.order), reads.n_reads, k,
                       self._p(n_pass), self._stream())
@@ -289,42 +306,97 @@ class Engine:
                 return table
             cap *= 2
 
-    def _count_docfreq_stream(self, reads, k, total_k, cap):
-        """Two-phase stage A: cfk_docfreq_emit (per-read sets in shared memory -> hash-partitioned records) and
-        cfk_docfreq_apply (records -> table, one L2-sized window of the table at a time).  Returns None when a
-        partition buffer overflowed (pathological hash skew): the caller falls back to the direct kernel."""
+    # -- two-phase stage A: cfk_docfreq_emit (reads -> hash-partitioned records) + cfk_docfreq_count_parts
+    def stream_plan(self, n_kmers, n_reads, n_ranks=1):
+        """(n_parts, part_cap) for n_kmers k-mer occurrences in n_reads reads on this rank; n_parts is a multiple of
+        n_ranks (partition range g of the exchange belongs to rank g).  A partition is planned for
+        cfk_docfreq_part_target() occurrences of the WHOLE job; its buffer also has room for three k-mers that occur in
+        every read (those add one record per read to a single partition)."""
+        target = int(self.lib.cfk_docfreq_part_target())
+        n_parts = max(1, -(-int(n_kmers) * n_ranks // target))
+        n_parts = -(-n_parts // n_ranks) * n_ranks
+        mean = -(-int(n_kmers) // n_parts)
+        part_cap = int(mean * self.part_slack) + 3 * min(int(n_reads), 16384) + 512
+        return n_parts, part_cap
+
+    def emit_records(self, reads, k, n_parts, part_cap, records=None, cursors=None, counters=None):
+        """Phase 1 -> (records int64[n_parts * part_cap], cursors int32[n_parts], counters)."""
         t = self.torch
         if reads.max_len >= (1 << 30):
-            return None  # the set's slots hold a 30-bit position
-        n_parts = int(self.lib.cfk_docfreq_parts())
+            raise CfkError("stage A (two-phase): reads of 2^30 bases or more are not supported")
         n_pass = self._empty(reads.n_reads, t.int32)
         _lib.call("cfk_docfreq_emit_plan", self._p(reads.read_len), self._p(reads.order), reads.n_reads, k,
                   self._p(n_pass), self._stream())
         item_ptr = self.exclusive_scan(n_pass[:reads.n_reads])
-        # records <= k-mer occurrences; the hash spreads them evenly (heavy k-mers: 2 records per read at most)
-        part_cap = min(int(total_k), int(total_k / n_parts * self.part_slack) + 4096) + 1
-        records = self._empty(n_parts * part_cap, t.int64)
-        cursors = self._zeros(n_parts, t.int64)
+        if records is None:
+            records = self._empty(n_parts * part_cap, t.int64)
+        if cursors is None:
+            cursors = self._zeros(n_parts, t.int32)
+        else:
+            cursors.zero_()
+        counters = self._counters() if counters is None else counters
+        with self._stage("docfreq_emit"):
+            _lib.call("cfk_docfreq_emit", self._p(reads.packed), self._p(reads.read_off), self._p(reads.read_len),
+                      self._p(reads.order), self._p(item_ptr), reads.n_reads, k, self._p(records), part_cap, n_parts,
+                      self._p(cursors), self._p(counters), self.n_sms, self._stream())
+        return records, cursors, counters
+
+    def count_records(self, records, cursors, n_parts, part_cap, band=None, with_counts=False, dense=None,
+                      n_src=1, src_stride=0, counters=None):
+        """Phase 2 over n_parts partitions -> (rare_keys, rare_nreads, rare_nmulti, counters, max_rare); the rare
+        outputs are None without a band.  `dense` (int64[2 * max_dense]) receives the whole table when given."""
+        t = self.torch
+        lo, hi, mn = (0, 0, 0) if band is None else band
+        hint_key = ("stream", bool(with_counts))
+        max_rare = int(self.select_hint.get(hint_key, 1 << 20)) if band is not None else 0
+        rare = self._empty(max_rare, t.int64) if band is not None else None
+        rare_nr = self._empty(max_rare, t.int32) if band is not None and with_counts else None
+        rare_nm = self._empty(max_rare, t.int32) if band is not None and with_counts else None
+        counters = self._counters() if counters is None else counters
+        with self._stage("docfreq_count"):
+            _lib.call("cfk_docfreq_count_parts", self._p(records), part_cap, self._p(cursors), n_parts, n_src, src_stride,
+                      int(lo), int(min(hi, U32_MAX)), int(min(mn, U32_MAX)), self._p(rare), self._p(rare_nr),
+                      self._p(rare_nm), max_rare, self._p(dense), 0 if dense is None else dense.numel() // 2,
+                      self._p(counters), self.n_sms, self._stream())
+        return rare, rare_nr, rare_nm, counters, max_rare
+
+    def docfreq_stream(self, reads, k, band=None, with_counts=False, want_table=False):
+        """Two-phase stage A on one GPU -> (rare, table) or None when a partition overflowed (pathological hash
+        skew, more than 65535 reads sharing a k-mer): the caller falls back to the single-kernel form.  rare = unordered
+        keys inside band = (lo, hi, max_nonuniq) (a tuple with the two count tensors when with_counts); table = the
+        dense DocFreqTable when want_table."""
+        t = self.torch
+        total_k = max(reads.n_bases - reads.n_reads * (k - 1), 0)
+        n_parts, part_cap = self.stream_plan(total_k, reads.n_reads)
+        records, cursors, counters = self.emit_records(reads, k, n_parts, part_cap)
+        dense = None
+        if want_table:
+            n_rec = int(cursors.sum(dtype=t.int64).item())  # distinct k-mers <= records
+            dense = self._empty(2 * max(n_rec, 1), t.int64)
         while True:
-            counters = self._counters()
-            with self._stage("docfreq_emit"):
-                _lib.call("cfk_docfreq_emit", self._p(reads.packed), self._p(reads.read_off), self._p(reads.read_len),
-                          self._p(reads.order), self._p(item_ptr), reads.n_reads, k, self._p(records), part_cap,
-                          self._p(cursors), self._p(counters), self.n_sms, self._stream())
-            table = self.new_table(cap)
-            with self._stage("docfreq_apply"):
-                _lib.call("cfk_docfreq_apply", self._p(records), part_cap, self._p(cursors), k, self._p(table.slots), cap,
-                          self._p(counters), self.n_sms, self._stream())
+            rare, rare_nr, rare_nm, counters, max_rare = self.count_records(records, cursors, n_parts, part_cap, band,
+                                                                            with_counts, dense, counters=counters)
             c = counters.cpu()
             if int(c[1]):
-                raise CfkError("stage A: per-read k-mer set overflowed (internal error)")
-            if int(c[0]) == 0:
-                self.last_docfreq_records = int(cursors.sum().item()) if self.events is not None else None
-                return table
-            if bool((cursors > part_cap).any().item()):
-                return None  # a partition buffer was too small: direct kernel
-            cap *= 2  # the table was: recount into a bigger one (the records are still valid, but keep it simple)
-            cursors.zero_()
+                raise CfkError("stage A: shared-memory set overflowed (internal error)")
+            if int(c[0]):
+                self.stream_fallbacks = getattr(self, "stream_fallbacks", 0) + 1
+                return None
+            n_rare = int(c[4])
+            if band is None or n_rare <= max_rare:
+                break
+            self.select_hint[("stream", bool(with_counts))] = n_rare + 1024  # the size is now known: phase 2 again
+            counters = self._counters()
+        table = None
+        if want_table:
+            n = int(c[5])
+            table = DocFreqTable(slots=dense[:2 * n], cap=n, dense=True)
+        if band is None:
+            return None, table
+        self.select_hint[("stream", bool(with_counts))] = max(max_rare, int(n_rare * 1.05) + 1024)
+        if with_counts:
+            return (rare[:n_rare], rare_nr[:n_rare], rare_nm[:n_rare]), table
+        return rare[:n_rare], table
 
     def count_total(self, reads, batch, k):
         """Total occurrences of every k-mer over all reads (no per-read de-duplication) -> DocFreqTable whose n_reads
@@ -375,6 +447,9 @@ class Engine:
     def table_lookup(self, table, keys):
         """(n_reads, n_multi) int32 tensors of the given keys (0 / 0 where the table does not hold the key)."""
         t = self.torch
+        if table.dense:
+            raise CfkError("table_lookup needs a hashed table; the two-phase stage A returns a dense one "
+                           "(use count_docfreq with docfreq_mode='resident')")
         n = int(keys.numel())
         nreads, nmulti = self._empty(n, t.int32), self._empty(n, t.int32)
         _lib.call("cfk_table_lookup", self._p(table.slots), table.cap, self._p(keys.contiguous()), n, self._p(nreads),
@@ -593,9 +668,7 @@ class Engine:
         """main() of the reference script on device-resident inputs; returns device-resident results.
         on_clouds(index, csr) is called as soon as the rare set and the clouds are final (before the distance graph):
         the place to start their trip to the host (start_host_copy)."""
-        table = self.count_docfreq(reads, k)
-        rare = self.table_select(table, lo, hi, max_nonuniq)
-        del table
+        rare = self.rare_kmers(reads, k, lo, hi, max_nonuniq)
         index = self.build_index(rare)
         csr = self.build_clouds(reads, units, k, index)
         if on_clouds is not None:

@@ -36,8 +36,8 @@ extern "C" {
 
 #define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define CFK_DOCFREQ_SET_SLOTS 49152 /* 32-bit slots of the per-read k-mer set in shared memory (192 KB) */
-#ifndef CFK_DOCFREQ_PART_BITS
-#define CFK_DOCFREQ_PART_BITS 7    /* log2 of the hash partitions of the two-phase stage A (cfk_docfreq_emit / _apply) */
+#ifndef CFK_DOCFREQ_PART_DISTINCT
+#define CFK_DOCFREQ_PART_DISTINCT 6144 /* distinct k-mers one hash partition of the two-phase stage A may hold */
 #endif
 #ifndef CFK_PAIR_WARPS
 #define CFK_PAIR_WARPS 20         /* warps per block of the stage-C kernel (one block per SM) */
@@ -99,28 +99,43 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
                                const int32_t* order, const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* table,
                                int64_t cap, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
 
-/* Two-phase form of stage A (the default path; same table, same results as cfk_docfreq_count).
- * Replaces get_kmer_freqs_from_ncrf_report, distance_based_kmer_recruitment.py:39-63, in two kernels:
- *   cfk_docfreq_emit   per (read, pass) item the per-read de-duplication of :50-53 runs in shared memory (the read
- *                      arrives by one cp.async.bulk copy; the set is built without atomics: claim, barrier, verify)
- *                      and ONE 8-byte record per distinct k-mer of the read -- bits 0..2k-1 the k-mer, bit 63 set if
- *                      the k-mer occurs in the read more than once (:55-56) -- is appended to hash partition
- *                      p = mix64(kmer) >> (64 - CFK_DOCFREQ_PART_BITS): records[p * part_cap + i], i < cursors[p].
- *   cfk_docfreq_apply  adds the records to the table partition by partition (n_reads += 1, n_multi += bit 63,
- *                      :57-62 in closed form); the home slot is monotone in the same hash, so a partition's updates
- *                      stay inside one 1/2^CFK_DOCFREQ_PART_BITS window of the table, i.e. in L2.
+/* Two-phase form of stage A (the default path of the engine; same counts as cfk_docfreq_count).
+ * Replaces get_kmer_freqs_from_ncrf_report, distance_based_kmer_recruitment.py:39-63, and the band of
+ * get_rare_kmers, :74-79, in two kernels and without a global hash table:
+ *   cfk_docfreq_emit         per (read, pass) item the per-read de-duplication of :50-53 runs in shared memory (the
+ *                            read arrives by one cp.async.bulk copy; the set is built without atomics: claim,
+ *                            barrier, verify) and ONE 8-byte record per distinct k-mer of the read -- bits 0..2k-1 the
+ *                            k-mer, bit 63 set if the k-mer occurs in the read more than once (:55-56) -- is appended
+ *                            to hash partition p = floor(hash32(kmer) * n_parts / 2^32):
+ *                            records[p * part_cap + i], i < cursors[p].
+ *   cfk_docfreq_count_parts  one block per partition adds the records up in a shared-memory table (n_reads += 1,
+ *                            n_multi += bit 63: :57-62 in closed form).  The partition's counts are final when its
+ *                            block ends, so the filter of get_rare_kmers runs in the same kernel: k-mers with
+ *                            n_multi <= max_nonuniq and lo <= n_reads <= hi go to rare_keys[] (+ rare_nreads[],
+ *                            rare_nmulti[] when given), unordered, counters[4] = how many (may exceed max_rare:
+ *                            nothing is written past it, the caller retries with more room).  dense != NULL: every
+ *                            distinct k-mer is also written as a 16-byte table slot { key ; n_reads | n_multi << 32 }
+ *                            without empty slots (a table for cfk_table_select / cfk_table_part_*), counters[5] =
+ *                            how many.  Records of one partition may come from n_src sources (the ranks of the
+ *                            multi-GPU exchange): source s holds records[s * src_stride + p * part_cap + i],
+ *                            i < cursors[s * n_parts + p].
  * cfk_docfreq_emit_plan writes n_pass[i] = passes of read order[i] (-> item_ptr by cfk_exclusive_scan).
- * cursors[cfk_docfreq_parts()] and counters[8] are zeroed by the caller.  counters: [0] != 0 a partition buffer
- * (emit) or the table (apply) overflowed -- results invalid, the caller grows / falls back; [1] != 0 internal set
- * overflow; [2], [3] work tickets. */
-int cfk_docfreq_parts(void);
+ * cfk_docfreq_part_target() = k-mer occurrences to plan per partition (n_parts = ceil(occurrences / target)); a
+ * partition may receive any number of records but must hold <= CFK_DOCFREQ_PART_DISTINCT distinct k-mers.
+ * cursors[] and counters[8] are zeroed by the caller.  counters[0] != 0: a partition buffer (emit) or a
+ * partition's table / 16-bit extra-read counter (count) overflowed -- results invalid, the caller falls back to
+ * cfk_docfreq_count_resident; [1] != 0 internal error; [2], [3] work tickets. */
+int cfk_docfreq_part_target(void);
 int cfk_docfreq_emit_plan(const int64_t* read_len, const int32_t* order, int64_t n_reads, int k, int32_t* n_pass,
                           cfk_stream_t stream);
 int cfk_docfreq_emit(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* order,
                      const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* records, int64_t part_cap,
-                     int64_t* cursors, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
-int cfk_docfreq_apply(const uint64_t* records, int64_t part_cap, const int64_t* cursors, int k, uint64_t* table, int64_t cap,
-                      int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
+                     int64_t n_parts, uint32_t* cursors, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
+int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, int64_t n_parts,
+                            int32_t n_src, int64_t src_stride, uint32_t lo, uint32_t hi, uint32_t max_nonuniq,
+                            uint64_t* rare_keys, uint32_t* rare_nreads, uint32_t* rare_nmulti, int64_t max_rare,
+                            uint64_t* dense, int64_t max_dense, int64_t* counters, int32_t n_blocks,
+                            cfk_stream_t stream);
 
 /* Total-occurrence count: replaces get_kmer_counts_reads,
  * scripts/better_consensus_unit_reconstruction.py:127-135 -- every k-mer occurrence of every gap-free read row adds 1
