@@ -113,6 +113,7 @@ class Engine:
         if self.docfreq_mode not in ("stream", "resident", "tiled"):
             raise CfkError(f"CFK_DOCFREQ_MODE must be stream, resident or tiled, got {self.docfreq_mode!r}")
         self.part_slack = 1.25  # records per partition buffer / expected records per partition (stream mode)
+        self.stream_group = 1   # partitions per phase-2 unit; adapted after every call (_adapt_stream_group)
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
         self._host_pool = {}  # name -> pinned uint8 buffer for results (to_host)
         self._copy_stream = None  # side stream of start_host_copy
@@ -319,6 +320,16 @@ class Engine:
         part_cap = int(mean * self.part_slack) + 3 * min(int(n_reads), 16384) + 512
         return n_parts, part_cap
 
+    def _adapt_stream_group(self, n_distinct, n_parts, n_retried):
+        """Partitions counted as one unit by the next phase 2: as many as keep a unit's distinct k-mers near 60 % of
+        the block's tables (any value is exact; a unit that does not fit is retried partition by partition)."""
+        cap = int(self.lib.cfk_docfreq_part_distinct())
+        per_part = max(1.0, n_distinct / max(1, n_parts))
+        group = int(max(1, min(64, 0.6 * cap / per_part)))
+        if n_retried * 20 > n_parts / max(1, self.stream_group):  # more than 5 % of the units did not fit
+            group = max(1, min(group, self.stream_group // 2))
+        self.stream_group = group
+
     def emit_records(self, reads, k, n_parts, part_cap, records=None, cursors=None, counters=None):
         """Phase 1 -> (records int64[n_parts * part_cap], cursors int32[n_parts], counters)."""
         t = self.torch
@@ -342,7 +353,7 @@ class Engine:
         return records, cursors, counters
 
     def count_records(self, records, cursors, n_parts, part_cap, band=None, with_counts=False, dense=None,
-                      n_src=1, src_stride=0, counters=None):
+                      n_src=1, src_stride=0, counters=None, group=1):
         """Phase 2 over n_parts partitions -> (rare_keys, rare_nreads, rare_nmulti, counters, max_rare); the rare
         outputs are None without a band.  `dense` (int64[2 * max_dense]) receives the whole table when given."""
         t = self.torch
@@ -355,7 +366,7 @@ class Engine:
         counters = self._counters() if counters is None else counters
         with self._stage("docfreq_count"):
             _lib.call("cfk_docfreq_count_parts", self._p(records), part_cap, self._p(cursors), n_parts, n_src, src_stride,
-                      int(lo), int(min(hi, U32_MAX)), int(min(mn, U32_MAX)), self._p(rare), self._p(rare_nr),
+                      int(group), int(lo), int(min(hi, U32_MAX)), int(min(mn, U32_MAX)), self._p(rare), self._p(rare_nr),
                       self._p(rare_nm), max_rare, self._p(dense), 0 if dense is None else dense.numel() // 2,
                       self._p(counters), self.n_sms, self._stream())
         return rare, rare_nr, rare_nm, counters, max_rare
@@ -375,7 +386,8 @@ class Engine:
             dense = self._empty(2 * max(n_rec, 1), t.int64)
         while True:
             rare, rare_nr, rare_nm, counters, max_rare = self.count_records(records, cursors, n_parts, part_cap, band,
-                                                                            with_counts, dense, counters=counters)
+                                                                            with_counts, dense, counters=counters,
+                                                                            group=self.stream_group)
             c = counters.cpu()
             if int(c[1]):
                 raise CfkError("stage A: shared-memory set overflowed (internal error)")
@@ -387,6 +399,7 @@ class Engine:
                 break
             self.select_hint[("stream", bool(with_counts))] = n_rare + 1024  # the size is now known: phase 2 again
             counters = self._counters()
+        self._adapt_stream_group(int(c[5]), n_parts, int(c[6]))
         table = None
         if want_table:
             n = int(c[5])

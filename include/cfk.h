@@ -37,7 +37,7 @@ extern "C" {
 #define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define CFK_DOCFREQ_SET_SLOTS 49152 /* 32-bit slots of the per-read k-mer set in shared memory (192 KB) */
 #ifndef CFK_DOCFREQ_PART_DISTINCT
-#define CFK_DOCFREQ_PART_DISTINCT 6144 /* distinct k-mers one hash partition of the two-phase stage A may hold */
+#define CFK_DOCFREQ_PART_DISTINCT 8192 /* distinct k-mers one unit (group of hash partitions) of the two-phase stage A may hold */
 #endif
 #ifndef CFK_PAIR_WARPS
 #define CFK_PAIR_WARPS 20         /* warps per block of the stage-C kernel (one block per SM) */
@@ -103,8 +103,8 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
  * Replaces get_kmer_freqs_from_ncrf_report, distance_based_kmer_recruitment.py:39-63, and the band of
  * get_rare_kmers, :74-79, in two kernels and without a global hash table:
  *   cfk_docfreq_emit         per (read, pass) item the per-read de-duplication of :50-53 runs in shared memory (the
- *                            read arrives by one cp.async.bulk copy; the set is built without atomics: claim,
- *                            barrier, verify) and ONE 8-byte record per distinct k-mer of the read -- bits 0..2k-1 the
+ *                            read arrives by one cp.async.bulk copy; probes are issued from warp-private queues so
+ *                            that every probe runs on a full warp) and ONE 8-byte record per distinct k-mer of the read -- bits 0..2k-1 the
  *                            k-mer, bit 63 set if the k-mer occurs in the read more than once (:55-56) -- is appended
  *                            to hash partition p = floor(hash32(kmer) * n_parts / 2^32):
  *                            records[p * part_cap + i], i < cursors[p].
@@ -116,7 +116,11 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
  *                            nothing is written past it, the caller retries with more room).  dense != NULL: every
  *                            distinct k-mer is also written as a 16-byte table slot { key ; n_reads | n_multi << 32 }
  *                            without empty slots (a table for cfk_table_select / cfk_table_part_*), counters[5] =
- *                            how many.  Records of one partition may come from n_src sources (the ranks of the
+ *                            how many (counted with or without dense).  `group` neighbouring partitions (= one
+ *                            wider hash range) are counted as one unit when their distinct k-mers fit the block's
+ *                            tables (CFK_DOCFREQ_PART_DISTINCT); a unit that does not fit is taken again partition by
+ *                            partition (counters[6] counts those), so any group >= 1 gives the same results.
+ *                            Records of one partition may come from n_src sources (the ranks of the
  *                            multi-GPU exchange): source s holds records[s * src_stride + p * part_cap + i],
  *                            i < cursors[s * n_parts + p].
  * cfk_docfreq_emit_plan writes n_pass[i] = passes of read order[i] (-> item_ptr by cfk_exclusive_scan).
@@ -124,17 +128,19 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
  * partition may receive any number of records but must hold <= CFK_DOCFREQ_PART_DISTINCT distinct k-mers.
  * cursors[] and counters[8] are zeroed by the caller.  counters[0] != 0: a partition buffer (emit) or a
  * partition's table / 16-bit extra-read counter (count) overflowed -- results invalid, the caller falls back to
- * cfk_docfreq_count_resident; [1] != 0 internal error; [2], [3] work tickets. */
+ * cfk_docfreq_count_resident; [1] != 0 internal error; [2], [3] work tickets.  The shared-memory sets claim empty
+ * slots with atomicCAS (a k-mer is in a set exactly once); everything else is plain loads and stores. */
 int cfk_docfreq_part_target(void);
+int cfk_docfreq_part_distinct(void); /* CFK_DOCFREQ_PART_DISTINCT of the built library */
 int cfk_docfreq_emit_plan(const int64_t* read_len, const int32_t* order, int64_t n_reads, int k, int32_t* n_pass,
                           cfk_stream_t stream);
 int cfk_docfreq_emit(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* order,
                      const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* records, int64_t part_cap,
                      int64_t n_parts, uint32_t* cursors, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
 int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, int64_t n_parts,
-                            int32_t n_src, int64_t src_stride, uint32_t lo, uint32_t hi, uint32_t max_nonuniq,
-                            uint64_t* rare_keys, uint32_t* rare_nreads, uint32_t* rare_nmulti, int64_t max_rare,
-                            uint64_t* dense, int64_t max_dense, int64_t* counters, int32_t n_blocks,
+                            int32_t n_src, int64_t src_stride, int32_t group, uint32_t lo, uint32_t hi,
+                            uint32_t max_nonuniq, uint64_t* rare_keys, uint32_t* rare_nreads, uint32_t* rare_nmulti,
+                            int64_t max_rare, uint64_t* dense, int64_t max_dense, int64_t* counters, int32_t n_blocks,
                             cfk_stream_t stream);
 
 /* Total-occurrence count: replaces get_kmer_counts_reads,
