@@ -384,24 +384,21 @@ docfreq_emit_kernel(const uint32_t* __restrict__ packed, const int64_t* __restri
 // phase 2
 // ================================================================================================================
 // One block per UNIT of `group` neighbouring partitions (tickets; neighbouring partitions are neighbouring hash
-// ranges, so their union is a partition too).  Shared memory: dk[] = the unit's distinct records so far followed by
-// the chunk being added, the set (slot id = index into dk + 1) and one 32-bit word per slot for the k-mers seen in
-// more than one read: low half = further reads, high half = how many of those held the k-mer more than once.  The
-// owner's own read is implicit (n_reads = 1 + low half, n_multi = bit 63 of the owner's record + high half).
-// Records arrive in chunks of CN_CHUNK; after a chunk its owners are compacted to the front of the chunk area (they
-// are the new distinct keys), so a unit made long by k-mers present in every read still needs room for its DISTINCT
-// keys only.  A unit with more distinct k-mers than CN_DCAP is taken again partition by partition.
+// ranges, so their union is a partition too).  Shared memory holds the unit's table: keys[] (64 bit: the record that
+// claimed the slot with atomicCAS -- k-mer in bits 0..61, bit 63 = that read held it more than once; all ones =
+// empty) and one 32-bit word per slot for the k-mers seen in more than one read: low half = further reads, high
+// half = how many of those held the k-mer more than once.  The owner's read is implicit (n_reads = 1 + low half,
+// n_multi = bit 63 + high half).  Records stream through registers, four in flight per thread, with no barrier
+// between the unit's first record and its last; buckets are two keys (one 16-byte load), linear probing over
+// buckets.  A unit with more distinct k-mers than the table takes is done again partition by partition.
 constexpr int CN_THREADS = 1024;
 constexpr int CN_PER = 4;
-constexpr int CN_CHUNK = CN_THREADS * CN_PER;  // records added per round
+constexpr int CN_CHUNK = CN_THREADS * CN_PER;  // records in flight per round
 constexpr int CN_DCAP = CFK_DOCFREQ_PART_DISTINCT;  // distinct k-mers a unit may hold
-constexpr int CN_NB = CN_DCAP / 3 + 1;         // 4-slot buckets: at most 75 % load
-constexpr int CN_SET_WORDS = ((4 * CN_NB + 3) / 4) * 4;
-constexpr uint32_t CN_ID_MASK = 0x3FFFu;       // 14 bits: index into dk + 1
-constexpr uint32_t CN_FP_MASK = 0x7FFFC000u;
+constexpr int CN_NB = CN_DCAP * 2 / 3;         // 2-key buckets: at most 75 % load
 constexpr uint64_t CN_KEY = 0x3FFFFFFFFFFFFFFFull;
-constexpr int CN_SMEM_BYTES = (CN_DCAP + CN_CHUNK) * 8 + CN_SET_WORDS * 4 * 2;
-static_assert(CN_DCAP + CN_CHUNK + 1 < (int)CN_ID_MASK, "slot id field");
+constexpr int CN_SMEM_BYTES = CN_NB * 2 * 12;
+constexpr int CN_MAX_PROBES = 96;              // buckets one record may visit before the unit is declared full
 static_assert(CN_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 __device__ __forceinline__ uint32_t cn_hash(uint64_t key) {
@@ -457,139 +454,108 @@ struct CountArgs {
 };
 
 struct CountSmem {
-  uint64_t* dk;
-  uint32_t* set;
+  uint64_t* keys;
   uint32_t* cnt;
   int* s_warp;
   int* s_abort;
   long long* s_base;
 };
 
-// partitions [p0, p1) as one unit; false: more distinct k-mers than the tables hold (nothing was written)
+// partitions [p0, p1) as one unit; false: more distinct k-mers than the table holds (nothing was written)
 __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int64_t p1) {
   const int lane = threadIdx.x & 31;
   int64_t n_unit = 0;  // records of the unit
   for (int64_t p = p0; p < p1; ++p)
     for (int32_t src = 0; src < A.n_src; ++src)
       n_unit += min((int64_t)__ldg(A.cursors + (int64_t)src * A.n_parts + p), A.part_cap);
-  // the set is sized for the unit: at most 75 % full even if every record is a new k-mer
-  const uint32_t nb = (uint32_t)min((int64_t)CN_NB, max((int64_t)64, n_unit / 3 + 1));
+  // the table is sized for the unit: at most 75 % full even if every record is a new k-mer
+  const uint32_t nb = (uint32_t)min((int64_t)CN_NB, max((int64_t)64, n_unit * 2 / 3 + 1));
   for (uint32_t i = threadIdx.x; i < nb; i += CN_THREADS) {
-    reinterpret_cast<uint4*>(S.set)[i] = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4*>(S.cnt)[i] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(S.keys)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    reinterpret_cast<uint2*>(S.cnt)[i] = make_uint2(0, 0);
   }
   if (threadIdx.x == 0) *S.s_abort = 0;
   __syncthreads();
-  int nd = 0;  // distinct records at the front of dk
-  int64_t seen = 0;
   for (int64_t p = p0; p < p1; ++p) {
     for (int32_t src = 0; src < A.n_src; ++src) {
       const int64_t n = min((int64_t)__ldg(A.cursors + (int64_t)src * A.n_parts + p), A.part_cap);
       const uint64_t* base = A.records + (int64_t)src * A.src_stride + p * A.part_cap;
       for (int64_t c0 = 0; c0 < n; c0 += CN_CHUNK) {
-        const int c = (int)min((int64_t)CN_CHUNK, n - c0);
-        seen += c;
-        const bool last = seen == n_unit;
+        if (*(volatile int*)S.s_abort) break;  // no barrier in here: every thread still reaches the one below
         uint64_t rec[CN_PER];
-        uint32_t fresh[CN_PER], b[CN_PER];
-        int own[CN_PER];
-        unsigned pend = 0, owner = 0;
+        uint32_t b[CN_PER];
+        unsigned pend = 0;
 #pragma unroll
         for (int j = 0; j < CN_PER; ++j) {
-          const int i = threadIdx.x + j * CN_THREADS;
+          const int64_t i = c0 + threadIdx.x + j * CN_THREADS;
           rec[j] = 0;
-          if (i < c) {
-            rec[j] = __ldcs(base + c0 + i);
-            S.dk[nd + i] = rec[j];
-            const uint32_t x = cn_hash(rec[j] & CN_KEY);
-            b[j] = __umulhi(x, nb);
-            fresh[j] = (uint32_t)(nd + i + 1) | ((x << 14) & CN_FP_MASK);
+          if (i < n) {
+            rec[j] = __ldcs(base + i);
+            b[j] = __umulhi(cn_hash(rec[j] & CN_KEY), nb);
             pend |= 1u << j;
           }
         }
-        __syncthreads();
-        // one walk per record: the k-mer is there -> its read goes to the entry's counter; else claim an empty slot
+        // one walk per record: the k-mer is there -> its read goes to the slot's counter; else claim an empty slot
         uint32_t rounds = 0;
-        while (__any_sync(FULL, pend != 0)) {
+        while (pend) {
 #pragma unroll
           for (int j = 0; j < CN_PER; ++j) {
             if (!((pend >> j) & 1u)) continue;
-            uint32_t* bucket = S.set + 4 * b[j];
-            const uint4 v4 = *reinterpret_cast<const uint4*>(bucket);
+            const uint4 v4 = reinterpret_cast<const uint4*>(S.keys)[b[j]];
             const uint64_t key = rec[j] & CN_KEY;
-            unsigned e = 0, m = 0;
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              const uint32_t x = pick4(v4, s);
-              if (x == 0) e |= 1u << s;
-              else if (((x ^ fresh[j]) & CN_FP_MASK) == 0) m |= 1u << s;
-            }
-            bool done = false;
-            while (m) {
-              const int s = __ffs(m) - 1;
-              m &= m - 1;
-              if ((S.dk[(pick4(v4, s) & CN_ID_MASK) - 1u] & CN_KEY) == key) {
-                const uint32_t old = atomicAdd(S.cnt + 4 * b[j] + s, 1u + (uint32_t)(rec[j] >> 63 << 16));
-                if ((old & 0xFFFFu) == 0xFFFFu) A.counters[0] = 2;  // 65536 further reads: the 16-bit halves are exhausted
-                done = true;
-                break;
+            const uint64_t k0 = (uint64_t)v4.x | ((uint64_t)v4.y << 32), k1 = (uint64_t)v4.z | ((uint64_t)v4.w << 32);
+            int hit = -1;  // slot of the bucket that holds the k-mer
+            if ((k0 & CN_KEY) == key) hit = 0;
+            else if (k0 == EMPTY) {
+              const uint64_t old = atomicCAS((unsigned long long*)(S.keys + 2 * b[j]), (unsigned long long)EMPTY,
+                                             (unsigned long long)rec[j]);
+              if (old == EMPTY) {
+                pend &= ~(1u << j);  // first read with this k-mer: the slot's owner
+                continue;
               }
+              if ((old & CN_KEY) == key) hit = 0;
             }
-            if (!done) {
-              if (e) {
-                const int s = __ffs(e) - 1;
-                if (atomicCAS(bucket + s, 0u, fresh[j]) == 0u) {  // lost: look at this bucket again
-                  own[j] = (int)(4 * b[j]) + s;
-                  owner |= 1u << j;
-                  done = true;
+            if (hit < 0) {
+              if ((k1 & CN_KEY) == key) hit = 1;
+              else if (k1 == EMPTY) {
+                const uint64_t old = atomicCAS((unsigned long long*)(S.keys + 2 * b[j] + 1), (unsigned long long)EMPTY,
+                                               (unsigned long long)rec[j]);
+                if (old == EMPTY) {
+                  pend &= ~(1u << j);
+                  continue;
                 }
-              } else {
-                b[j] = (b[j] + 1 == nb) ? 0u : b[j] + 1;
+                if ((old & CN_KEY) == key) hit = 1;
               }
             }
-            if (done) pend &= ~(1u << j);
+            if (hit >= 0) {
+              const uint32_t old = atomicAdd(S.cnt + 2 * b[j] + hit, 1u + (uint32_t)(rec[j] >> 63 << 16));
+              if ((old & 0xFFFFu) == 0xFFFFu) A.counters[0] = 2;  // 65536 further reads: the 16-bit halves are exhausted
+              pend &= ~(1u << j);
+            } else {
+              b[j] = (b[j] + 1 == nb) ? 0u : b[j] + 1;
+            }
           }
-          if (++rounds > 4 * (uint32_t)CN_NB + 64) {  // the set is full
+          if (++rounds > CN_MAX_PROBES) {  // the table is (nearly) full
             *S.s_abort = 1;
             break;
           }
         }
-        __syncthreads();
-        if (*S.s_abort) return false;  // block-uniform: read behind the barrier, never written after it
-        if (!last) {
-          // the chunk's owners move to the front of the chunk area: they are the new distinct keys
-          int total = 0;
-          int rank = cn_block_scan(__popc(owner), &total, S.s_warp);
-#pragma unroll
-          for (int j = 0; j < CN_PER; ++j) {
-            if (!((owner >> j) & 1u)) continue;
-            const int at = nd + rank++;
-            if (at < CN_DCAP + CN_CHUNK) {
-              S.dk[at] = rec[j];
-              S.set[own[j]] = (uint32_t)(at + 1) | (fresh[j] & CN_FP_MASK);
-            }
-          }
-          nd += total;
-          __syncthreads();
-          if (nd > CN_DCAP) return false;  // block-uniform
-        }
       }
     }
   }
+  __syncthreads();
+  if (*S.s_abort) return false;  // block-uniform: read behind the barrier, not written after it
   // ---- output: every occupied slot is one distinct k-mer with its final counts
-  const uint32_t n_slots = 4 * nb;
+  const uint32_t n_slots = 2 * nb;
   int n_live = 0;
   for (uint32_t s0 = 0; s0 < n_slots; s0 += CN_THREADS) {  // block-uniform trip count
     const uint32_t s = s0 + threadIdx.x;
-    const uint32_t v = s < n_slots ? S.set[s] : 0u;
+    const uint64_t r = s < n_slots ? S.keys[s] : EMPTY;
     bool take = false;
-    uint64_t key = 0;
     uint32_t nr = 0, nm = 0;
-    if (v != 0) {
+    if (r != EMPTY) {
       ++n_live;
-      const uint64_t r = S.dk[(v & CN_ID_MASK) - 1u];
       const uint32_t cw = S.cnt[s];
-      key = r & CN_KEY;
       nr = 1u + (cw & 0xFFFFu);
       nm = (uint32_t)(r >> 63) + (cw >> 16);
       take = A.rare_keys != nullptr && nm <= A.max_nonuniq && nr >= A.lo && nr <= A.hi;
@@ -600,7 +566,7 @@ __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int6
     if (lane == __ffs(m) - 1) at = (long long)atomicAdd((unsigned long long*)(A.counters + 4), (unsigned long long)__popc(m));
     at = __shfl_sync(FULL, at, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
     if (take && at < A.max_rare) {
-      A.rare_keys[at] = key;
+      A.rare_keys[at] = r & CN_KEY;
       if (A.rare_nreads != nullptr) A.rare_nreads[at] = nr;
       if (A.rare_nmulti != nullptr) A.rare_nmulti[at] = nm;
     }
@@ -613,9 +579,8 @@ __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int6
       __syncthreads();
       long long at = *S.s_base + rank;
       for (uint32_t s = threadIdx.x; s < n_slots; s += CN_THREADS) {
-        const uint32_t v = S.set[s];
-        if (v == 0) continue;
-        const uint64_t r = S.dk[(v & CN_ID_MASK) - 1u];
+        const uint64_t r = S.keys[s];
+        if (r == EMPTY) continue;
         const uint32_t cw = S.cnt[s];
         if (at < A.max_dense)
           A.dense[at] = make_uint4((uint32_t)r, (uint32_t)(r >> 32) & 0x3FFFFFFFu, 1u + (cw & 0xFFFFu), (uint32_t)(r >> 63) + (cw >> 16));
@@ -623,7 +588,7 @@ __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int6
       }
     }
   }
-  __syncthreads();  // the tables are cleared by the next unit
+  __syncthreads();  // the table is cleared by the next unit
   return true;
 }
 
@@ -633,9 +598,8 @@ __global__ void __launch_bounds__(CN_THREADS, 1) docfreq_count_kernel(const Coun
   __shared__ long long s_ticket, s_base;
   __shared__ int s_abort;
   CountSmem S;
-  S.dk = reinterpret_cast<uint64_t*>(cn_smem);
-  S.set = cn_smem + 2 * (CN_DCAP + CN_CHUNK);
-  S.cnt = S.set + CN_SET_WORDS;
+  S.keys = reinterpret_cast<uint64_t*>(cn_smem);
+  S.cnt = cn_smem + 4 * CN_NB;
   S.s_warp = s_warp;
   S.s_abort = &s_abort;
   S.s_base = &s_base;

@@ -37,7 +37,7 @@ extern "C" {
 #define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define CFK_DOCFREQ_SET_SLOTS 49152 /* 32-bit slots of the per-read k-mer set in shared memory (192 KB) */
 #ifndef CFK_DOCFREQ_PART_DISTINCT
-#define CFK_DOCFREQ_PART_DISTINCT 8192 /* distinct k-mers one unit (group of hash partitions) of the two-phase stage A may hold */
+#define CFK_DOCFREQ_PART_DISTINCT 9216 /* distinct k-mers one unit (group of hash partitions) of the two-phase stage A may hold */
 #endif
 #ifndef CFK_PAIR_WARPS
 #define CFK_PAIR_WARPS 20         /* warps per block of the stage-C kernel (one block per SM) */
