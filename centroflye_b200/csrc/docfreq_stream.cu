@@ -39,7 +39,7 @@ __device__ __forceinline__ uint32_t pick4(const uint4& v, int s) { return s == 0
 // phase 1
 // ================================================================================================================
 #ifndef CFK_DE_FILL_PCT
-#define CFK_DE_FILL_PCT 72   /* planned load of the per-read set, percent (4-slot buckets) */
+#define CFK_DE_FILL_PCT 85   /* planned load of the per-read set, percent (4-slot buckets) */
 #endif
 #ifndef CFK_DE_THREADS
 #define CFK_DE_THREADS 1024
@@ -263,6 +263,7 @@ __device__ __forceinline__ void de_scan_emit(const uint32_t* words, const uint32
   const uint64_t mask = (1ull << (2 * k)) - 1;
   const int pos_bits = 64 - __clzll((unsigned long long)(nk + 1));
   const uint32_t pos_mask = (1u << pos_bits) - 1u;
+  const bool small = (uint64_t)n_parts * part_cap < (1ull << 32);
   for (uint32_t b = threadIdx.x; b < nb; b += DE_THREADS) {
     const uint4 v4 = *reinterpret_cast<const uint4*>(set + 4 * b);
     uint64_t rec[4];
@@ -276,7 +277,7 @@ __device__ __forceinline__ void de_scan_emit(const uint32_t* words, const uint32
       if (v != 0) {
         const uint64_t raw = de_raw_at<IN_SMEM>(words, (v & pos_mask) - 1u, mask);
         part[s] = __umulhi(de_hash(raw), n_parts);
-        rec[s] = de_key_of_raw(raw, k) | ((uint64_t)(v >> 31) << 63);
+        rec[s] = raw | ((uint64_t)(v >> 31) << 63);  // records keep the raw order: phase 2 turns distinct k-mers into keys
         live |= 1u << s;
       }
     }
@@ -297,11 +298,20 @@ __device__ __forceinline__ void de_scan_emit(const uint32_t* words, const uint32
     if (f2) idx[2] = idx[1] + 1;
     if (f3) idx[3] = idx[2] + 1;
     bool over = false;
+    if (small) {  // the whole record array has fewer than 2^32 entries: 32-bit offsets
 #pragma unroll
-    for (int s = 0; s < 4; ++s) {
-      if (!((live >> s) & 1u)) continue;
-      if (idx[s] < part_cap) records[(uint64_t)part[s] * part_cap + idx[s]] = rec[s];
-      else over = true;
+      for (int s = 0; s < 4; ++s) {
+        if (!((live >> s) & 1u)) continue;
+        if (idx[s] < part_cap) records[part[s] * part_cap + idx[s]] = rec[s];
+        else over = true;
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (!((live >> s) & 1u)) continue;
+        if (idx[s] < part_cap) records[(uint64_t)part[s] * part_cap + idx[s]] = rec[s];
+        else over = true;
+      }
     }
     if (over) counters[0] = 1;  // partition buffer full: the host falls back (never silent)
   }
@@ -391,7 +401,10 @@ docfreq_emit_kernel(const uint32_t* __restrict__ packed, const int64_t* __restri
 // n_multi = bit 63 + high half).  Records stream through registers, four in flight per thread, with no barrier
 // between the unit's first record and its last; buckets are two keys (one 16-byte load), linear probing over
 // buckets.  A unit with more distinct k-mers than the table takes is done again partition by partition.
-constexpr int CN_THREADS = 1024;
+#ifndef CFK_CN_THREADS
+#define CFK_CN_THREADS 256
+#endif
+constexpr int CN_THREADS = CFK_CN_THREADS;  // 1024 / CN_THREADS blocks share an SM
 constexpr int CN_PER = 4;
 constexpr int CN_CHUNK = CN_THREADS * CN_PER;  // records in flight per round
 constexpr int CN_DCAP = CFK_DOCFREQ_PART_DISTINCT;  // distinct k-mers a unit may hold
@@ -399,7 +412,7 @@ constexpr int CN_NB = CN_DCAP * 2 / 3;         // 2-key buckets: at most 75 % lo
 constexpr uint64_t CN_KEY = 0x3FFFFFFFFFFFFFFFull;
 constexpr int CN_SMEM_BYTES = CN_NB * 2 * 12;
 constexpr int CN_MAX_PROBES = 96;              // buckets one record may visit before the unit is declared full
-static_assert(CN_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(CN_SMEM_BYTES <= 227 * 1024 / (1024 / CN_THREADS) - 1024, "shared memory budget");
 
 __device__ __forceinline__ uint32_t cn_hash(uint64_t key) {
   uint32_t x = (uint32_t)key * 0x9E3779B1u + (uint32_t)(key >> 32) * 0x85EBCA77u;
@@ -421,7 +434,7 @@ __device__ __forceinline__ int cn_block_scan(int v, int* total, int* s_warp /* [
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    const int w = s_warp[lane];
+    const int w = lane < CN_THREADS / 32 ? s_warp[lane] : 0;
     int wi = w;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -442,7 +455,7 @@ struct CountArgs {
   const uint64_t* records;
   const uint32_t* cursors;
   int64_t part_cap, n_parts, src_stride;
-  int32_t n_src, group;
+  int32_t n_src, group, k;
   uint32_t lo, hi, max_nonuniq;
   uint64_t* rare_keys;
   uint32_t* rare_nreads;
@@ -461,15 +474,16 @@ struct CountSmem {
   long long* s_base;
 };
 
-// partitions [p0, p1) as one unit; false: more distinct k-mers than the table holds (nothing was written)
-__device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int64_t p1) {
+// partitions [p0, p1) as one unit, restricted to the records whose hash has `sub` in its low bits (n_sub a power of
+// two; 0, 1 = all records); false: more distinct k-mers than the table holds (nothing was written)
+__device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int64_t p1, uint32_t sub, uint32_t n_sub) {
   const int lane = threadIdx.x & 31;
   int64_t n_unit = 0;  // records of the unit
   for (int64_t p = p0; p < p1; ++p)
     for (int32_t src = 0; src < A.n_src; ++src)
       n_unit += min((int64_t)__ldg(A.cursors + (int64_t)src * A.n_parts + p), A.part_cap);
   // the table is sized for the unit: at most 75 % full even if every record is a new k-mer
-  const uint32_t nb = (uint32_t)min((int64_t)CN_NB, max((int64_t)64, n_unit * 2 / 3 + 1));
+  const uint32_t nb = (uint32_t)min((int64_t)CN_NB, max((int64_t)64, n_unit * 2 / 3 + 1));  // (also right for a sub-range)
   for (uint32_t i = threadIdx.x; i < nb; i += CN_THREADS) {
     reinterpret_cast<uint4*>(S.keys)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
     reinterpret_cast<uint2*>(S.cnt)[i] = make_uint2(0, 0);
@@ -491,8 +505,9 @@ __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int6
           rec[j] = 0;
           if (i < n) {
             rec[j] = __ldcs(base + i);
-            b[j] = __umulhi(cn_hash(rec[j] & CN_KEY), nb);
-            pend |= 1u << j;
+            const uint32_t x = cn_hash(rec[j] & CN_KEY);
+            b[j] = __umulhi(x, nb);
+            if ((x & (n_sub - 1u)) == sub) pend |= 1u << j;
           }
         }
         // one walk per record: the k-mer is there -> its read goes to the slot's counter; else claim an empty slot
@@ -566,7 +581,7 @@ __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int6
     if (lane == __ffs(m) - 1) at = (long long)atomicAdd((unsigned long long*)(A.counters + 4), (unsigned long long)__popc(m));
     at = __shfl_sync(FULL, at, __ffs(m) - 1) + __popc(m & ((1u << lane) - 1u));
     if (take && at < A.max_rare) {
-      A.rare_keys[at] = r & CN_KEY;
+      A.rare_keys[at] = de_key_of_raw(r & CN_KEY, A.k);
       if (A.rare_nreads != nullptr) A.rare_nreads[at] = nr;
       if (A.rare_nmulti != nullptr) A.rare_nmulti[at] = nm;
     }
@@ -582,8 +597,9 @@ __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int6
         const uint64_t r = S.keys[s];
         if (r == EMPTY) continue;
         const uint32_t cw = S.cnt[s];
+        const uint64_t key = de_key_of_raw(r & CN_KEY, A.k);
         if (at < A.max_dense)
-          A.dense[at] = make_uint4((uint32_t)r, (uint32_t)(r >> 32) & 0x3FFFFFFFu, 1u + (cw & 0xFFFFu), (uint32_t)(r >> 63) + (cw >> 16));
+          A.dense[at] = make_uint4((uint32_t)key, (uint32_t)(key >> 32), 1u + (cw & 0xFFFFu), (uint32_t)(r >> 63) + (cw >> 16));
         ++at;
       }
     }
@@ -592,7 +608,7 @@ __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int6
   return true;
 }
 
-__global__ void __launch_bounds__(CN_THREADS, 1) docfreq_count_kernel(const CountArgs A) {
+__global__ void __launch_bounds__(CN_THREADS, 1024 / CN_THREADS) docfreq_count_kernel(const CountArgs A) {
   extern __shared__ __align__(16) uint32_t cn_smem[];
   __shared__ int s_warp[33];
   __shared__ long long s_ticket, s_base;
@@ -611,17 +627,32 @@ __global__ void __launch_bounds__(CN_THREADS, 1) docfreq_count_kernel(const Coun
     const int64_t u = s_ticket;
     if (u >= n_units) break;
     const int64_t p0 = u * A.group, p1 = min(p0 + (int64_t)A.group, A.n_parts);
-    if (cn_unit(A, S, p0, p1)) continue;
-    __syncthreads();
-    if (p1 - p0 > 1) {  // too many distinct k-mers for one table: partition by partition
-      if (threadIdx.x == 0) atomicAdd((unsigned long long*)(A.counters + 6), 1ull);
-      bool ok = true;
-      for (int64_t p = p0; p < p1; ++p) {
+    if (cn_unit(A, S, p0, p1, 0u, 1u)) continue;
+    // too many distinct k-mers for one table: partition by partition, and a partition that still does not fit by
+    // halves of its hash range (every record is read once per attempt; the results do not depend on the split)
+    if (threadIdx.x == 0) atomicAdd((unsigned long long*)(A.counters + 6), 1ull);
+    bool ok = true;
+    for (int64_t p = p0; p < p1 && ok; ++p) {
+      __syncthreads();
+      if (p1 - p0 > 1 && cn_unit(A, S, p, p + 1, 0u, 1u)) continue;
+      uint32_t st_sub[8], st_n[8];
+      int top = 0;
+      st_sub[top] = 0u, st_n[top++] = 2u;
+      st_sub[top] = 1u, st_n[top++] = 2u;
+      while (top > 0 && ok) {
+        --top;
+        const uint32_t sub = st_sub[top], n_sub = st_n[top];
         __syncthreads();
-        ok = cn_unit(A, S, p, p + 1) && ok;
+        if (cn_unit(A, S, p, p + 1, sub, n_sub)) continue;
+        if (n_sub >= 64u) {
+          ok = false;
+        } else {
+          st_sub[top] = sub, st_n[top++] = 2u * n_sub;
+          st_sub[top] = sub + n_sub, st_n[top++] = 2u * n_sub;
+        }
       }
-      if (ok) continue;
     }
+    if (ok) continue;
     if (threadIdx.x == 0) A.counters[0] = 1;  // one partition holds more distinct k-mers than planned: the host falls back
   }
 }
@@ -664,10 +695,11 @@ int cfk_docfreq_emit(const uint32_t* packed, const int64_t* read_off, const int6
 }
 
 int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, int64_t n_parts,
-                            int32_t n_src, int64_t src_stride, int32_t group, uint32_t lo, uint32_t hi,
+                            int32_t n_src, int64_t src_stride, int32_t group, int k, uint32_t lo, uint32_t hi,
                             uint32_t max_nonuniq, uint64_t* rare_keys, uint32_t* rare_nreads, uint32_t* rare_nmulti,
                             int64_t max_rare, uint64_t* dense, int64_t max_dense, int64_t* counters, int32_t n_blocks,
                             cfk_stream_t stream) {
+  if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_docfreq_count_parts: k must be in [1, 31]");
   if (part_cap < 1 || n_parts < 0 || n_src < 1 || group < 1 || n_blocks < 1 || max_rare < 0 || max_dense < 0)
     return fail(CFK_ERR_INVALID, "cfk_docfreq_count_parts: bad sizes");
   if (n_parts == 0) return CFK_OK;
@@ -684,6 +716,7 @@ int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uin
   A.src_stride = src_stride;
   A.n_src = n_src;
   A.group = group;
+  A.k = k;
   A.lo = lo;
   A.hi = hi;
   A.max_nonuniq = max_nonuniq;
@@ -695,7 +728,8 @@ int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uin
   A.max_dense = max_dense;
   A.counters = counters;
   const int64_t n_units = (n_parts + group - 1) / group;
-  const int64_t grid = n_units < n_blocks ? n_units : n_blocks;
+  const int64_t want = (int64_t)n_blocks * (1024 / CN_THREADS);
+  const int64_t grid = n_units < want ? n_units : want;
   docfreq_count_kernel<<<(unsigned)grid, CN_THREADS, CN_SMEM_BYTES, (cudaStream_t)stream>>>(A);
   CFK_CHECK_LAUNCH("docfreq_count_kernel", 1);
   return CFK_OK;

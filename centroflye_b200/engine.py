@@ -352,7 +352,7 @@ class Engine:
                       self._p(cursors), self._p(counters), self.n_sms, self._stream())
         return records, cursors, counters
 
-    def count_records(self, records, cursors, n_parts, part_cap, band=None, with_counts=False, dense=None,
+    def count_records(self, records, cursors, n_parts, part_cap, k, band=None, with_counts=False, dense=None,
                       n_src=1, src_stride=0, counters=None, group=1):
         """Phase 2 over n_parts partitions -> (rare_keys, rare_nreads, rare_nmulti, counters, max_rare); the rare
         outputs are None without a band.  `dense` (int64[2 * max_dense]) receives the whole table when given."""
@@ -366,7 +366,7 @@ class Engine:
         counters = self._counters() if counters is None else counters
         with self._stage("docfreq_count"):
             _lib.call("cfk_docfreq_count_parts", self._p(records), part_cap, self._p(cursors), n_parts, n_src, src_stride,
-                      int(group), int(lo), int(min(hi, U32_MAX)), int(min(mn, U32_MAX)), self._p(rare), self._p(rare_nr),
+                      int(group), int(k), int(lo), int(min(hi, U32_MAX)), int(min(mn, U32_MAX)), self._p(rare), self._p(rare_nr),
                       self._p(rare_nm), max_rare, self._p(dense), 0 if dense is None else dense.numel() // 2,
                       self._p(counters), self.n_sms, self._stream())
         return rare, rare_nr, rare_nm, counters, max_rare
@@ -385,7 +385,7 @@ class Engine:
             n_rec = int(cursors.sum(dtype=t.int64).item())  # distinct k-mers <= records
             dense = self._empty(2 * max(n_rec, 1), t.int64)
         while True:
-            rare, rare_nr, rare_nm, counters, max_rare = self.count_records(records, cursors, n_parts, part_cap, band,
+            rare, rare_nr, rare_nm, counters, max_rare = self.count_records(records, cursors, n_parts, part_cap, k, band,
                                                                             with_counts, dense, counters=counters,
                                                                             group=self.stream_group)
             c = counters.cpu()

@@ -37,7 +37,7 @@ extern "C" {
 #define CFK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 #define CFK_DOCFREQ_SET_SLOTS 49152 /* 32-bit slots of the per-read k-mer set in shared memory (192 KB) */
 #ifndef CFK_DOCFREQ_PART_DISTINCT
-#define CFK_DOCFREQ_PART_DISTINCT 9216 /* distinct k-mers one unit (group of hash partitions) of the two-phase stage A may hold */
+#define CFK_DOCFREQ_PART_DISTINCT 2304 /* distinct k-mers one unit (group of hash partitions) of the two-phase stage A holds at a time */
 #endif
 #ifndef CFK_PAIR_WARPS
 #define CFK_PAIR_WARPS 20         /* warps per block of the stage-C kernel (one block per SM) */
@@ -105,7 +105,9 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
  *   cfk_docfreq_emit         per (read, pass) item the per-read de-duplication of :50-53 runs in shared memory (the
  *                            read arrives by one cp.async.bulk copy; probes are issued from warp-private queues so
  *                            that every probe runs on a full warp) and ONE 8-byte record per distinct k-mer of the read -- bits 0..2k-1 the
- *                            k-mer, bit 63 set if the k-mer occurs in the read more than once (:55-56) -- is appended
+ *                            k-mer in the order the packed read holds it (base j of the k-mer at bits 2j..2j+1; phase 2
+ *                            turns the distinct k-mers into keys), bit 63 set if the k-mer occurs in the read more
+ *                            than once (:55-56) -- is appended
  *                            to hash partition p = floor(hash32(kmer) * n_parts / 2^32):
  *                            records[p * part_cap + i], i < cursors[p].
  *   cfk_docfreq_count_parts  one block per partition adds the records up in a shared-memory table (n_reads += 1,
@@ -138,7 +140,7 @@ int cfk_docfreq_emit(const uint32_t* packed, const int64_t* read_off, const int6
                      const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* records, int64_t part_cap,
                      int64_t n_parts, uint32_t* cursors, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
 int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, int64_t n_parts,
-                            int32_t n_src, int64_t src_stride, int32_t group, uint32_t lo, uint32_t hi,
+                            int32_t n_src, int64_t src_stride, int32_t group, int k, uint32_t lo, uint32_t hi,
                             uint32_t max_nonuniq, uint64_t* rare_keys, uint32_t* rare_nreads, uint32_t* rare_nmulti,
                             int64_t max_rare, uint64_t* dense, int64_t max_dense, int64_t* counters, int32_t n_blocks,
                             cfk_stream_t stream);
