@@ -297,10 +297,10 @@ def run_ours(args):
     pair_kernel = getattr(eng, "last_pair_kernel", "pair_candidates_kernel")
     traffic, traffic_src = ncu_traffic(pair_kernel)
     # the other kernels of the step against the same HBM line (algorithmic bytes of BASELINE.md §4, rank 0's share)
-    df_kernel = {"stream": "docfreq_emit_kernel+docfreq_apply_kernel", "resident": "docfreq_resident_kernel"}.get(
+    df_kernel = {"stream": "docfreq_emit_kernel+docfreq_count_kernel", "resident": "docfreq_resident_kernel"}.get(
         eng.docfreq_mode, "docfreq_kernel")
-    if eng.docfreq_mode == "stream":  # two kernels: the stage-A figure is their sum
-        stage_ms["docfreq"] = [a + b for a, b in zip(stage_ms.get("docfreq_emit", []), stage_ms.get("docfreq_apply", []))]
+    if eng.docfreq_mode == "stream" and "docfreq_emit" in stage_ms:  # two kernels: the stage-A figure is their sum
+        stage_ms["docfreq"] = [a + b for a, b in zip(stage_ms.get("docfreq_emit", []), stage_ms.get("docfreq_count", []))]
     n_k = int(batch.n_bases - batch.n_reads * (k - 1))
     n_ku = int(units.unit_len.astype(np.int64).sum() - units.n_units * (k - 1))
     csr_last = res[1]

@@ -36,7 +36,7 @@ def pytest_collection_modifyitems(config, items):
 
 
 def golden_cases():
-    return sorted(d for d in os.listdir(GOLDEN) if os.path.isdir(os.path.join(GOLDEN, d)))
+    return sorted(d for d in os.listdir(GOLDEN) if os.path.exists(os.path.join(GOLDEN, d, "report.ncrf.gz")))
 
 
 def golden_points(case):
