@@ -29,7 +29,8 @@ SIGNATURES = {
     "cfk_docfreq_part_distinct": (_int, []),
     "cfk_docfreq_emit_plan": (_int, [_p, _p, _i64, _int, _p, _p]),
     "cfk_docfreq_emit": (_int, [_p, _p, _p, _p, _p, _i64, _int, _p, _i64, _i64, _p, _p, _i32, _p]),
-    "cfk_docfreq_count_parts": (_int, [_p, _i64, _p, _i64, _i32, _i64, _i32, _int, _u32, _u32, _u32, _p, _p, _p, _i64, _p,
+    "cfk_records_pack": (_int, [_p, _i64, _p, _p, _i64, _p, _p]),
+    "cfk_docfreq_count_parts": (_int, [_p, _i64, _p, _p, _i64, _i32, _i64, _i32, _int, _u32, _u32, _u32, _p, _p, _p, _i64, _p,
                                        _i64, _p, _i32, _p]),
     "cfk_kmer_count_tile": (_int, []),
     "cfk_kmer_count_total": (_int, [_p, _p, _p, _p, _p, _i64, _int, _p, _i64, _p, _p]),

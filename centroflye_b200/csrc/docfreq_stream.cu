@@ -454,6 +454,7 @@ __device__ __forceinline__ int cn_block_scan(int v, int* total, int* s_warp /* [
 struct CountArgs {
   const uint64_t* records;
   const uint32_t* cursors;
+  const int64_t* offsets;  // not NULL: records of (source, partition) start at offsets[source * n_parts + partition] (dense runs)
   int64_t part_cap, n_parts, src_stride;
   int32_t n_src, group, k;
   uint32_t lo, hi, max_nonuniq;
@@ -465,6 +466,11 @@ struct CountArgs {
   int64_t max_dense;
   int64_t* counters;
 };
+
+__device__ __forceinline__ int64_t cn_run_len(const CountArgs& A, int32_t src, int64_t p) {
+  const int64_t n = (int64_t)__ldg(A.cursors + (int64_t)src * A.n_parts + p);
+  return A.offsets != nullptr ? n : min(n, A.part_cap);
+}
 
 struct CountSmem {
   uint64_t* keys;
@@ -481,7 +487,7 @@ __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int6
   int64_t n_unit = 0;  // records of the unit
   for (int64_t p = p0; p < p1; ++p)
     for (int32_t src = 0; src < A.n_src; ++src)
-      n_unit += min((int64_t)__ldg(A.cursors + (int64_t)src * A.n_parts + p), A.part_cap);
+      n_unit += cn_run_len(A, src, p);
   // the table is sized for the unit: at most 75 % full even if every record is a new k-mer
   const uint32_t nb = (uint32_t)min((int64_t)CN_NB, max((int64_t)64, n_unit * 2 / 3 + 1));  // (also right for a sub-range)
   for (uint32_t i = threadIdx.x; i < nb; i += CN_THREADS) {
@@ -492,8 +498,9 @@ __device__ bool cn_unit(const CountArgs& A, const CountSmem& S, int64_t p0, int6
   __syncthreads();
   for (int64_t p = p0; p < p1; ++p) {
     for (int32_t src = 0; src < A.n_src; ++src) {
-      const int64_t n = min((int64_t)__ldg(A.cursors + (int64_t)src * A.n_parts + p), A.part_cap);
-      const uint64_t* base = A.records + (int64_t)src * A.src_stride + p * A.part_cap;
+      const int64_t n = cn_run_len(A, src, p);
+      const uint64_t* base = A.offsets != nullptr ? A.records + __ldg(A.offsets + (int64_t)src * A.n_parts + p)
+                                                  : A.records + (int64_t)src * A.src_stride + p * A.part_cap;
       for (int64_t c0 = 0; c0 < n; c0 += CN_CHUNK) {
         if (*(volatile int*)S.s_abort) break;  // no barrier in here: every thread still reaches the one below
         uint64_t rec[CN_PER];
@@ -657,6 +664,20 @@ __global__ void __launch_bounds__(CN_THREADS, 1024 / CN_THREADS) docfreq_count_k
   }
 }
 
+// records[p * part_cap + i], i < cursors[p]  ->  out[offsets[p] + i]: the partitions back to back (the send buffer of
+// the multi-GPU exchange; offsets = exclusive scan of the cursors).  One block per partition.
+__global__ void __launch_bounds__(256) records_pack_kernel(const uint64_t* __restrict__ records, int64_t part_cap,
+                                                           const uint32_t* __restrict__ cursors,
+                                                           const int64_t* __restrict__ offsets, int64_t n_parts,
+                                                           uint64_t* __restrict__ out) {
+  for (int64_t p = blockIdx.x; p < n_parts; p += gridDim.x) {
+    const int64_t n = min((int64_t)__ldg(cursors + p), part_cap);
+    const uint64_t* src = records + p * part_cap;
+    uint64_t* dst = out + __ldg(offsets + p);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcs(src + i);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -694,8 +715,18 @@ int cfk_docfreq_emit(const uint32_t* packed, const int64_t* read_off, const int6
   return CFK_OK;
 }
 
-int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, int64_t n_parts,
-                            int32_t n_src, int64_t src_stride, int32_t group, int k, uint32_t lo, uint32_t hi,
+int cfk_records_pack(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, const int64_t* offsets,
+                     int64_t n_parts, uint64_t* out, cfk_stream_t stream) {
+  if (part_cap < 1 || n_parts < 0) return fail(CFK_ERR_INVALID, "cfk_records_pack: bad sizes");
+  if (n_parts == 0) return CFK_OK;
+  const int64_t grid = n_parts < 148 * 16 ? n_parts : 148 * 16;
+  records_pack_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(records, part_cap, cursors, offsets, n_parts, out);
+  CFK_CHECK_LAUNCH("records_pack_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, const int64_t* offsets,
+                            int64_t n_parts, int32_t n_src, int64_t src_stride, int32_t group, int k, uint32_t lo, uint32_t hi,
                             uint32_t max_nonuniq, uint64_t* rare_keys, uint32_t* rare_nreads, uint32_t* rare_nmulti,
                             int64_t max_rare, uint64_t* dense, int64_t max_dense, int64_t* counters, int32_t n_blocks,
                             cfk_stream_t stream) {
@@ -711,6 +742,7 @@ int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uin
   CountArgs A;
   A.records = records;
   A.cursors = cursors;
+  A.offsets = offsets;
   A.part_cap = part_cap;
   A.n_parts = n_parts;
   A.src_stride = src_stride;

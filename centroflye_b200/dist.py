@@ -3,10 +3,12 @@
 The reference is single-process; this is the partitioning of SURVEY.md §8e:
 
   reads         sharded by record across ranks (every rank holds whole reads and their units)
-  stage A       local document-frequency table -> hash partition (cfk_table_part_*) -> all-to-all of
-                (key, n_reads, n_multi) records -> the owner sums them (cfk_table_merge), applies max_nonuniq
-                and the rare band, and the rare keys are all-gathered, so every rank holds the same sorted set
-                (n_reads and n_multi are sums over reads, dbkr.py:55-59, hence additive over read shards)
+  stage A       phase 1 of the two-phase kernel pair on the rank's own reads (one 8-byte record per distinct k-mer of
+                a read, in n_parts hash partitions) -> all-to-all of the records, partition range g to rank g ->
+                phase 2 on the owned partitions with one record run per source rank: n_reads / n_multi of the WHOLE
+                read set, max_nonuniq and the rare band in the same kernel -> the rare keys are all-gathered, so
+                every rank holds the same sorted set (n_reads and n_multi are sums over reads, dbkr.py:55-59, hence
+                additive over read shards).  The earlier table-based exchanges are kept for docfreq_mode != stream.
   stage B       local: clouds of the rank's own units against the global rare set
   stage C/D     the cloud CSR is all-gathered (units concatenated in rank order) and the SOURCE k-mer ids are
                 dealt round-robin: rank r handles a = r, r + G, ...  No counter ever crosses a rank boundary
@@ -16,6 +18,9 @@ The collectives are written against torch.distributed only (all_to_all_single, a
 exchange logic below runs unchanged on gloo/CPU tensors (tests/test_dist_gloo.py) and NCCL/CUDA tensors.
 """
 import numpy as np
+
+from . import _lib
+from ._lib import CfkError
 
 U32_MAX = 0xFFFFFFFF
 _GOLDEN = np.uint64(0x9E3779B97F4A7C15)
@@ -75,6 +80,35 @@ def all_gather_v(t, group=None):
     return torch.cat(parts) if parts else t.new_empty(0), counts
 
 
+def exchange_records(send, part_counts, world, group=None, flags=None):
+    """The record all-to-all of stage A.  `send` holds this rank's records with the partitions back to back
+    (partition p: part_counts[p] records), n_parts = world * parts_per_rank, partition range g goes to rank g.
+    Returns (recv, recv_counts, flags, n_sent): recv = the records of this rank's partition range, source-major
+    (source 0's run of partitions, then source 1's ...), recv_counts[s * parts_per_rank + q] = records of local
+    partition q from source s -- exactly the (records, cursors) layout cfk_docfreq_count_parts takes with offsets =
+    exclusive scan of recv_counts.  One host sync (the split sizes); `flags` (small int64 tensor) rides along and
+    comes back as a python list, all-reduced with MAX; n_sent = records this rank sent."""
+    import torch
+    import torch.distributed as dist
+    n_parts = int(part_counts.numel())
+    per = n_parts // world
+    recv_counts = torch.empty_like(part_counts)
+    dist.all_to_all_single(recv_counts, part_counts.contiguous(), group=group)
+    sizes = torch.stack([part_counts.view(world, per).sum(1, dtype=torch.int64),
+                         recv_counts.view(world, per).sum(1, dtype=torch.int64)]).reshape(-1)
+    if flags is not None:
+        flags = flags.to(torch.int64).clone()
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+        sizes = torch.cat([sizes, flags])
+    host = sizes.cpu().tolist()
+    n_send, n_recv = host[:world], host[world:2 * world]
+    recv = send.new_empty(max(int(sum(n_recv)), 1))
+    dist.all_to_all_single(recv[: int(sum(n_recv))], send[: int(sum(n_send))].contiguous(),
+                           output_split_sizes=[int(c) for c in n_recv], input_split_sizes=[int(c) for c in n_send],
+                           group=group)
+    return recv, recv_counts, host[2 * world:], int(sum(n_send))
+
+
 def merge_cloud_shards(cnt_all, unit_counts, last_all):
     """Per-rank (|cloud| per unit, index of the last unit of the read, local numbering) -> global numbering.
 
@@ -99,14 +133,63 @@ class ShardedRecruiter:
         self.batch, self.units = batch, units
         self.reads = engine.upload_reads(batch, k)
         self.dunits = engine.upload_units(units, k)
-        n = torch.tensor([batch.n_bases], dtype=torch.int64, device=engine.device)
+        self.n_kmers_local = int(np.maximum(batch.read_len - k + 1, 0).sum())
+        n = torch.tensor([batch.n_bases, self.n_kmers_local], dtype=torch.int64, device=engine.device)
         dist.all_reduce(n, group=group)
-        self.n_bases_total = int(n.item())
+        self.n_bases_total, self.n_kmers_total = int(n[0].item()), int(n[1].item())
         self.last_increments = 0
         self.bytes_exchanged = 0
         self.nominate = True  # stage A exchange: nominate-then-sum (False: all-to-all of every table record)
 
     # ---- stage A exchange ---------------------------------------------------------------------------------
+    def global_rare_stream(self, lo, hi, max_nonuniq):
+        """Two-phase stage A over all ranks -> sorted rare keys of the WHOLE read set (identical on every rank), or
+        None when phase 2 could not hold a partition (the caller falls back to the table-based exchange).
+        emit (local reads) -> pack -> all-to-all of the records (partition range g to rank g) -> count with one record
+        run per source rank -> all-gather of the rare keys.  Two host syncs: the split sizes, and phase 2's counters."""
+        eng, t, W = self.eng, self.torch, self.world
+        if lo > hi or max_nonuniq < 0:
+            return eng._empty(0, t.int64)[:0]
+        n_parts, part_cap = eng.stream_plan(self.n_kmers_total, self.reads.n_reads, n_ranks=W,
+                                            n_kmers_local=self.n_kmers_local)
+        per = n_parts // W
+        for attempt in range(3):
+            records, cursors, ecounters = eng.emit_records(self.reads, self.k, n_parts, part_cap)
+            with eng._stage("exchange_docfreq"):
+                counts = cursors.clamp(max=part_cap)
+                offsets = eng.exclusive_scan(counts)
+                send = eng._empty(self.n_kmers_local, t.int64)  # records <= k-mer occurrences
+                _lib.call("cfk_records_pack", eng._p(records), part_cap, eng._p(counts), eng._p(offsets), n_parts,
+                          eng._p(send), eng._stream())
+                recv, recv_counts, flags, n_sent = exchange_records(send, counts, W, self.group,
+                                                                    flags=eng.emit_stats(cursors, ecounters))
+            self.bytes_exchanged += 8 * n_sent + 4 * n_parts
+            if flags[1]:
+                raise CfkError("stage A: per-read k-mer set overflowed (internal error)")
+            if not flags[0]:
+                break
+            biggest = int(cursors.max().item())  # some rank ran out of room: all ranks go again with what they measured
+            eng.part_cap_seen[n_parts] = max(eng.part_cap_seen.get(n_parts, 0), biggest)
+            part_cap = max(part_cap, int(biggest * 1.05) + 256)
+            del records, send, recv
+        else:
+            raise CfkError("stage A: partition buffers overflowed three times (internal error)")
+        roff = eng.exclusive_scan(recv_counts)
+        band = (lo, hi, max_nonuniq)
+        out = eng.finish_count(lambda counters: eng.count_records(recv, recv_counts, per, 1, self.k, band, n_src=W,
+                                                                  offsets=roff, counters=counters, group=eng.stream_group),
+                               band, False)
+        ok = t.tensor([0 if out is None else 1], dtype=t.int64, device=eng.device)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 0:
+            return None
+        mine, c = out
+        eng._adapt_stream_group(int(c[5]), per, int(c[6]))
+        with eng._stage("exchange_docfreq"):
+            allk, _ = all_gather_v(mine.contiguous(), self.group)
+            self.bytes_exchanged += 8 * int(mine.numel())
+        return eng.sort_keys(allk.clone()) if allk.numel() else allk
+
     def global_rare_keys(self, table, lo, hi, max_nonuniq):
         """Local table -> sorted rare keys of the WHOLE read set (identical on every rank).
 
@@ -166,10 +249,12 @@ class ShardedRecruiter:
         on_clouds(index, csr) is called as soon as the rare set and this rank's clouds are final."""
         from .engine import DistResult
         eng, t = self.eng, self.torch
-        table = eng._count_docfreq_direct(self.reads, self.k)  # hashed table: the exchange looks keys up
-        with eng._stage("exchange_docfreq"):
-            rare = self.global_rare_keys(table, lo, hi, max_nonuniq)
-        del table
+        rare = self.global_rare_stream(lo, hi, max_nonuniq) if eng.docfreq_mode == "stream" else None
+        if rare is None:
+            table = eng._count_docfreq_direct(self.reads, self.k)  # hashed table: this exchange looks keys up
+            with eng._stage("exchange_docfreq"):
+                rare = self.global_rare_keys(table, lo, hi, max_nonuniq)
+            del table
         index = eng.build_index(rare, presorted=True)
         csr = eng.build_clouds(self.reads, self.dunits, self.k, index)
         if on_clouds is not None:

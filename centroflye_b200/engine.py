@@ -114,6 +114,7 @@ class Engine:
             raise CfkError(f"CFK_DOCFREQ_MODE must be stream, resident or tiled, got {self.docfreq_mode!r}")
         self.part_slack = 1.25  # records per partition buffer / expected records per partition (stream mode)
         self.stream_group = 1   # partitions per phase-2 unit; adapted after every call (_adapt_stream_group)
+        self.part_cap_seen = {}  # n_parts -> largest partition (records) phase 1 produced so far
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
         self._host_pool = {}  # name -> pinned uint8 buffer for results (to_host)
         self._copy_stream = None  # side stream of start_host_copy
@@ -308,30 +309,25 @@ class Engine:
             cap *= 2
 
     # -- two-phase stage A: cfk_docfreq_emit (reads -> hash-partitioned records) + cfk_docfreq_count_parts
-    def stream_plan(self, n_kmers, n_reads, n_ranks=1):
-        """(n_parts, part_cap) for n_kmers k-mer occurrences in n_reads reads on this rank; n_parts is a multiple of
-        n_ranks (partition range g of the exchange belongs to rank g).  A partition is planned for
-        cfk_docfreq_part_target() occurrences of the WHOLE job; its buffer also has room for three k-mers that occur in
-        every read (those add one record per read to a single partition)."""
+    def stream_plan(self, n_kmers, n_reads, n_ranks=1, n_kmers_local=None):
+        """(n_parts, part_cap): n_parts hash partitions for n_kmers k-mer occurrences of the WHOLE job (a multiple of
+        n_ranks: partition range g of the exchange belongs to rank g), each planned for cfk_docfreq_part_target()
+        occurrences; part_cap = records one partition buffer of THIS rank holds.  The first guess leaves room for two
+        k-mers present in every local read on top of the mean; a call whose buffers overflowed is repeated with the
+        size it measured, and later calls start from the largest size seen (self.part_cap_seen)."""
         target = int(self.lib.cfk_docfreq_part_target())
-        n_parts = max(1, -(-int(n_kmers) * n_ranks // target))
+        n_parts = max(1, -(-int(n_kmers) // target))
         n_parts = -(-n_parts // n_ranks) * n_ranks
-        mean = -(-int(n_kmers) // n_parts)
-        part_cap = int(mean * self.part_slack) + 3 * min(int(n_reads), 16384) + 512
-        return n_parts, part_cap
+        local = int(n_kmers if n_kmers_local is None else n_kmers_local)
+        mean = -(-local // n_parts)
+        guess = int(mean * self.part_slack) + 2 * min(int(n_reads), 16384) + 512
+        seen = self.part_cap_seen.get(n_parts)
+        part_cap = int(seen * 1.1) + 256 if seen else guess
+        return n_parts, max(1, min(part_cap, local + 1))
 
-    def _adapt_stream_group(self, n_distinct, n_parts, n_retried):
-        """Partitions counted as one unit by the next phase 2: as many as keep a unit's distinct k-mers near 60 % of
-        the block's tables (any value is exact; a unit that does not fit is retried partition by partition)."""
-        cap = int(self.lib.cfk_docfreq_part_distinct())
-        per_part = max(1.0, n_distinct / max(1, n_parts))
-        group = int(max(1, min(64, 0.6 * cap / per_part)))
-        if n_retried * 20 > n_parts / max(1, self.stream_group):  # more than 5 % of the units did not fit
-            group = max(1, min(group, self.stream_group // 2))
-        self.stream_group = group
-
-    def emit_records(self, reads, k, n_parts, part_cap, records=None, cursors=None, counters=None):
-        """Phase 1 -> (records int64[n_parts * part_cap], cursors int32[n_parts], counters)."""
+    def emit_records(self, reads, k, n_parts, part_cap):
+        """Phase 1 -> (records int64[n_parts * part_cap], cursors int32[n_parts], counters).  counters[0] != 0:
+        some partition buffer was too small (cursors then hold the sizes that would have been needed)."""
         t = self.torch
         if reads.max_len >= (1 << 30):
             raise CfkError("stage A (two-phase): reads of 2^30 bases or more are not supported")
@@ -339,13 +335,9 @@ class Engine:
         _lib.call("cfk_docfreq_emit_plan", self._p(reads.read_len), self._p(reads.order), reads.n_reads, k,
                   self._p(n_pass), self._stream())
         item_ptr = self.exclusive_scan(n_pass[:reads.n_reads])
-        if records is None:
-            records = self._empty(n_parts * part_cap, t.int64)
-        if cursors is None:
-            cursors = self._zeros(n_parts, t.int32)
-        else:
-            cursors.zero_()
-        counters = self._counters() if counters is None else counters
+        records = self._empty(n_parts * part_cap, t.int64)
+        cursors = self._zeros(n_parts, t.int32)
+        counters = self._counters()
         with self._stage("docfreq_emit"):
             _lib.call("cfk_docfreq_emit", self._p(reads.packed), self._p(reads.read_off), self._p(reads.read_len),
                       self._p(reads.order), self._p(item_ptr), reads.n_reads, k, self._p(records), part_cap, n_parts,
@@ -353,7 +345,7 @@ class Engine:
         return records, cursors, counters
 
     def count_records(self, records, cursors, n_parts, part_cap, k, band=None, with_counts=False, dense=None,
-                      n_src=1, src_stride=0, counters=None, group=1):
+                      n_src=1, src_stride=0, offsets=None, counters=None, group=1):
         """Phase 2 over n_parts partitions -> (rare_keys, rare_nreads, rare_nmulti, counters, max_rare); the rare
         outputs are None without a band.  `dense` (int64[2 * max_dense]) receives the whole table when given."""
         t = self.torch
@@ -365,32 +357,35 @@ class Engine:
         rare_nm = self._empty(max_rare, t.int32) if band is not None and with_counts else None
         counters = self._counters() if counters is None else counters
         with self._stage("docfreq_count"):
-            _lib.call("cfk_docfreq_count_parts", self._p(records), part_cap, self._p(cursors), n_parts, n_src, src_stride,
-                      int(group), int(k), int(lo), int(min(hi, U32_MAX)), int(min(mn, U32_MAX)), self._p(rare), self._p(rare_nr),
-                      self._p(rare_nm), max_rare, self._p(dense), 0 if dense is None else dense.numel() // 2,
-                      self._p(counters), self.n_sms, self._stream())
+            _lib.call("cfk_docfreq_count_parts", self._p(records), part_cap, self._p(cursors), self._p(offsets), n_parts,
+                      n_src, src_stride, int(group), int(k), int(lo), int(min(hi, U32_MAX)), int(min(mn, U32_MAX)),
+                      self._p(rare), self._p(rare_nr), self._p(rare_nm), max_rare, self._p(dense),
+                      0 if dense is None else dense.numel() // 2, self._p(counters), self.n_sms, self._stream())
         return rare, rare_nr, rare_nm, counters, max_rare
 
-    def docfreq_stream(self, reads, k, band=None, with_counts=False, want_table=False):
-        """Two-phase stage A on one GPU -> (rare, table) or None when a partition overflowed (pathological hash
-        skew, more than 65535 reads sharing a k-mer): the caller falls back to the single-kernel form.  rare = unordered
-        keys inside band = (lo, hi, max_nonuniq) (a tuple with the two count tensors when with_counts); table = the
-        dense DocFreqTable when want_table."""
+    def _adapt_stream_group(self, n_distinct, n_parts, n_retried):
+        """Partitions counted as one unit by the next phase 2: as many as keep a unit's distinct k-mers near 60 % of
+        the block's table (any value is exact; a unit that does not fit is retried partition by partition)."""
+        cap = int(self.lib.cfk_docfreq_part_distinct())
+        per_part = max(1.0, n_distinct / max(1, n_parts))
+        group = int(max(1, min(64, 0.6 * cap / per_part)))
+        if n_retried * 20 > n_parts / max(1, self.stream_group):  # more than 5 % of the units did not fit
+            group = max(1, min(group, self.stream_group // 2))
+        self.stream_group = group
+
+    def finish_count(self, run_count, band, with_counts, extra=None):
+        """Runs phase 2 (run_count(counters) -> the tuple of count_records) until its rare output fits; ONE host sync
+        per run brings its counters (and `extra`, a small int64 device tensor, appended).  Returns (rare outputs, host
+        counters + extra) or None when a partition did not fit phase 2 at all."""
         t = self.torch
-        total_k = max(reads.n_bases - reads.n_reads * (k - 1), 0)
-        n_parts, part_cap = self.stream_plan(total_k, reads.n_reads)
-        records, cursors, counters = self.emit_records(reads, k, n_parts, part_cap)
-        dense = None
-        if want_table:
-            n_rec = int(cursors.sum(dtype=t.int64).item())  # distinct k-mers <= records
-            dense = self._empty(2 * max(n_rec, 1), t.int64)
+        counters = self._counters()
         while True:
-            rare, rare_nr, rare_nm, counters, max_rare = self.count_records(records, cursors, n_parts, part_cap, k, band,
-                                                                            with_counts, dense, counters=counters,
-                                                                            group=self.stream_group)
-            c = counters.cpu()
+            rare, rare_nr, rare_nm, counters, max_rare = run_count(counters)
+            c = (counters if extra is None else t.cat([counters, extra])).cpu()
             if int(c[1]):
                 raise CfkError("stage A: shared-memory set overflowed (internal error)")
+            if extra is not None and int(c[8]):
+                return "emit-overflow", c  # phase 1 ran out of room: these results are void
             if int(c[0]):
                 self.stream_fallbacks = getattr(self, "stream_fallbacks", 0) + 1
                 return None
@@ -399,17 +394,56 @@ class Engine:
                 break
             self.select_hint[("stream", bool(with_counts))] = n_rare + 1024  # the size is now known: phase 2 again
             counters = self._counters()
+        if band is None:
+            return None, c
+        self.select_hint[("stream", bool(with_counts))] = max(max_rare, int(n_rare * 1.05) + 1024)
+        if with_counts:
+            return (rare[:n_rare], rare_nr[:n_rare], rare_nm[:n_rare]), c
+        return rare[:n_rare], c
+
+    def emit_stats(self, cursors, counters):
+        """int64[3] device tensor: phase 1's overflow flag, its internal-error flag, its largest partition."""
+        t = self.torch
+        return t.stack([counters[0], counters[1], cursors.max().to(t.int64)])
+
+    def docfreq_stream(self, reads, k, band=None, with_counts=False, want_table=False):
+        """Two-phase stage A on one GPU -> (rare, table) or None when phase 2 could not hold a partition (more than
+        65535 reads sharing a k-mer, or a partition that does not fit after 64-fold splitting): the caller falls back
+        to the single-kernel form.  rare = unordered keys inside band = (lo, hi, max_nonuniq) (a tuple with the two
+        count tensors when with_counts); table = the dense DocFreqTable when want_table.  One host sync at the end
+        (two when the table is wanted: its size comes from phase 1)."""
+        t = self.torch
+        total_k = max(reads.n_bases - reads.n_reads * (k - 1), 0)
+        n_parts, part_cap = self.stream_plan(total_k, reads.n_reads)
+        for attempt in range(3):
+            records, cursors, ecounters = self.emit_records(reads, k, n_parts, part_cap)
+            dense = None
+            if want_table:
+                n_rec = int(cursors.clamp(max=part_cap).sum(dtype=t.int64).item())  # distinct k-mers <= records
+                dense = self._empty(2 * max(n_rec, 1), t.int64)
+            out = self.finish_count(lambda counters: self.count_records(records, cursors, n_parts, part_cap, k, band,
+                                                                        with_counts, dense, counters=counters,
+                                                                        group=self.stream_group),
+                                    band, with_counts, extra=self.emit_stats(cursors, ecounters))
+            if out is None:
+                return None
+            rare, c = out
+            if int(c[9]):
+                raise CfkError("stage A: per-read k-mer set overflowed (internal error)")
+            biggest = int(c[10])
+            self.part_cap_seen[n_parts] = max(self.part_cap_seen.get(n_parts, 0), biggest)
+            if not (isinstance(rare, str) and rare == "emit-overflow"):
+                break
+            del records, dense  # a partition buffer was too small: once more with the size phase 1 measured
+            part_cap = int(biggest * 1.05) + 256
+        else:
+            raise CfkError("stage A: partition buffers overflowed three times (internal error)")
         self._adapt_stream_group(int(c[5]), n_parts, int(c[6]))
         table = None
         if want_table:
             n = int(c[5])
             table = DocFreqTable(slots=dense[:2 * n], cap=n, dense=True)
-        if band is None:
-            return None, table
-        self.select_hint[("stream", bool(with_counts))] = max(max_rare, int(n_rare * 1.05) + 1024)
-        if with_counts:
-            return (rare[:n_rare], rare_nr[:n_rare], rare_nm[:n_rare]), table
-        return rare[:n_rare], table
+        return rare, table
 
     def count_total(self, reads, batch, k):
         """Total occurrences of every k-mer over all reads (no per-read de-duplication) -> DocFreqTable whose n_reads

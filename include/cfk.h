@@ -124,7 +124,9 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
  *                            partition (counters[6] counts those), so any group >= 1 gives the same results.
  *                            Records of one partition may come from n_src sources (the ranks of the
  *                            multi-GPU exchange): source s holds records[s * src_stride + p * part_cap + i],
- *                            i < cursors[s * n_parts + p].
+ *                            i < cursors[s * n_parts + p]; or, with offsets != NULL, dense runs
+ *                            records[offsets[s * n_parts + p] + i] (what the exchange delivers: cfk_records_pack
+ *                            lays a rank's partitions back to back, out[offsets[p] + i], before the all-to-all).
  * cfk_docfreq_emit_plan writes n_pass[i] = passes of read order[i] (-> item_ptr by cfk_exclusive_scan).
  * cfk_docfreq_part_target() = k-mer occurrences to plan per partition (n_parts = ceil(occurrences / target)); a
  * partition may receive any number of records but must hold <= CFK_DOCFREQ_PART_DISTINCT distinct k-mers.
@@ -132,6 +134,8 @@ int cfk_docfreq_count_resident(const uint32_t* packed, const int64_t* read_off, 
  * partition's table / 16-bit extra-read counter (count) overflowed -- results invalid, the caller falls back to
  * cfk_docfreq_count_resident; [1] != 0 internal error; [2], [3] work tickets.  The shared-memory sets claim empty
  * slots with atomicCAS (a k-mer is in a set exactly once); everything else is plain loads and stores. */
+int cfk_records_pack(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, const int64_t* offsets,
+                     int64_t n_parts, uint64_t* out, cfk_stream_t stream);
 int cfk_docfreq_part_target(void);
 int cfk_docfreq_part_distinct(void); /* CFK_DOCFREQ_PART_DISTINCT of the built library */
 int cfk_docfreq_emit_plan(const int64_t* read_len, const int32_t* order, int64_t n_reads, int k, int32_t* n_pass,
@@ -139,8 +143,8 @@ int cfk_docfreq_emit_plan(const int64_t* read_len, const int32_t* order, int64_t
 int cfk_docfreq_emit(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* order,
                      const int64_t* item_ptr, int64_t n_reads, int k, uint64_t* records, int64_t part_cap,
                      int64_t n_parts, uint32_t* cursors, int64_t* counters, int32_t n_blocks, cfk_stream_t stream);
-int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, int64_t n_parts,
-                            int32_t n_src, int64_t src_stride, int32_t group, int k, uint32_t lo, uint32_t hi,
+int cfk_docfreq_count_parts(const uint64_t* records, int64_t part_cap, const uint32_t* cursors, const int64_t* offsets,
+                            int64_t n_parts, int32_t n_src, int64_t src_stride, int32_t group, int k, uint32_t lo, uint32_t hi,
                             uint32_t max_nonuniq, uint64_t* rare_keys, uint32_t* rare_nreads, uint32_t* rare_nmulti,
                             int64_t max_rare, uint64_t* dense, int64_t max_dense, int64_t* counters, int32_t n_blocks,
                             cfk_stream_t stream);

@@ -42,14 +42,21 @@ def main():
     lo, hi = band_to_int(0.9 * 20 * 0.4, 3.0 * 20 * 0.4)
     batch, units = batch_from_synth(mine, len(unit))
     rec = ShardedRecruiter(eng, batch, units, k, rank, world)
-    rec.nominate = False  # the full all-to-all of table records ...
+    eng.docfreq_mode = "resident"  # the table-based exchanges: the full all-to-all of table records ...
+    rec.nominate = False
     index_full, _, _ = rec.step(lo, hi, max_nonuniq, min_d, max_d, min_cov)
     full_bytes, rec.bytes_exchanged = rec.bytes_exchanged, 0
-    rec.nominate = True   # ... and the nominate-then-sum exchange give the same rare set
-    index, csr, res = rec.step(lo, hi, max_nonuniq, min_d, max_d, min_cov)
-    keys = index.sorted_keys.cpu().numpy().view(np.uint64)
-    assert np.array_equal(keys, index_full.sorted_keys.cpu().numpy().view(np.uint64)), "the two stage-A exchanges disagree"
+    rec.nominate = True   # ... and nominate-then-sum give the same rare set
+    index_nom, _, _ = rec.step(lo, hi, max_nonuniq, min_d, max_d, min_cov)
+    assert np.array_equal(index_nom.sorted_keys.cpu().numpy(), index_full.sorted_keys.cpu().numpy()), "the two table exchanges disagree"
     assert rec.bytes_exchanged < full_bytes
+    eng.docfreq_mode = "stream"    # the default: all-to-all of phase 1's records, phase 2 on the owned partitions
+    rec.bytes_exchanged = 0
+    for _ in range(2):  # the second step runs with the adapted partition grouping / buffer sizes
+        index, csr, res = rec.step(lo, hi, max_nonuniq, min_d, max_d, min_cov)
+    keys = index.sorted_keys.cpu().numpy().view(np.uint64)
+    assert getattr(eng, "stream_fallbacks", 0) == 0, "the record exchange fell back"
+    assert np.array_equal(keys, index_full.sorted_keys.cpu().numpy().view(np.uint64)), "record exchange != table exchange"
 
     whole_batch, whole_units = batch_from_synth(reads, len(unit))
     want = c_oracle.recruit(whole_batch, whole_units, k, lo, hi, max_nonuniq, min_d, max_d, min_cov, threads=2)
