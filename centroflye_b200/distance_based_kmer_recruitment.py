@@ -202,7 +202,10 @@ def _count_table(reads_ncrf_report, k):
 def get_kmer_freqs_from_ncrf_report(reads_ncrf_report, k, verbose, max_nonuniq):
     k = check_k(k)
     engine, table = _count_table(reads_ncrf_report, k)
-    keys, nreads, _ = engine.table_select(table, 0, U32_MAX, max_nonuniq, with_counts=True)
+    if max_nonuniq < 0:  # dbkr.py:57-62: every k-mer fails `non_unique_freqs[kmer] <= max_nonuniq` and is deleted
+        keys, nreads = engine._empty(0, engine.torch.int64)[:0], engine._empty(0, engine.torch.int32)[:0]
+    else:
+        keys, nreads, _ = engine.table_select(table, 0, U32_MAX, max_nonuniq, with_counts=True)
     if verbose:
         print(len(reads_ncrf_report.records), len(reads_ncrf_report.records))
     return KmerFreqs(to_host_u64(keys), to_host_u32(nreads), k, table=table, engine=engine)
@@ -210,11 +213,12 @@ def get_kmer_freqs_from_ncrf_report(reads_ncrf_report, k, verbose, max_nonuniq):
 
 def get_rare_kmers(reads_ncrf_report, k, bottom, top, coverage, kmer_survival_rate, max_nonuniq, verbose):
     k = check_k(k)
-    engine, table = _count_table(reads_ncrf_report, k)
+    engine = default_engine()
+    reads = report_device_reads(reads_ncrf_report, engine, k)
     left = bottom*coverage*kmer_survival_rate   # float64, this order (dbkr.py:74-75)
     right = top*coverage*kmer_survival_rate
     lo, hi = band_to_int(left, right)
-    rare_keys = engine.table_select(table, lo, hi, max_nonuniq) if lo <= hi else engine._empty(0, engine.torch.int64)[:0]
+    rare_keys = engine.rare_kmers(reads, k, lo, hi, max_nonuniq)  # counting and band in one device pass
     index = engine.build_index(rare_keys)
     rare = RareKmerSet(ints_to_kmers(to_host_u64(index.sorted_keys), k))
     rare._cfk_index = (engine, index)
@@ -322,11 +326,17 @@ def write_edges_native(path, kmer_index, dist_edges, threads=0):
         raise OSError(lib.cfk_writer_last_error().decode(errors="replace"))
 
 
+LAST_TIMINGS = {}  # wall-clock seconds of the stages of the last main() call (bench.py reports them as e2e_cli)
+
+
 def main(argv=None):
+    import time
+    stamp = [("start", time.perf_counter())]
     params = parse_args(argv)
     smart_makedirs(params.outdir)
 
     reads_ncrf_report = NCRF_Report(params.ncrf)
+    stamp.append(("parse_report", time.perf_counter()))
     rare_kmers = get_rare_kmers(reads_ncrf_report,
                                 k=params.k,
                                 bottom=params.bottom,
@@ -336,7 +346,10 @@ def main(argv=None):
                                 max_nonuniq=params.max_nonuniq,
                                 verbose=params.verbose)
 
+    stamp.append(("ingest_count_rare", time.perf_counter()))
+
     reads_kmer_clouds = get_reads_kmer_clouds(reads_ncrf_report, n=1, k=params.k, genomic_kmers=rare_kmers)
+    stamp.append(("clouds", time.perf_counter()))
 
     dist_cnt, kmer_index = get_kmer_dist_map(reads_kmer_clouds, rare_kmers,
                                              min_n=params.min_nreads, max_n=params.max_nreads,
@@ -344,9 +357,14 @@ def main(argv=None):
                                              verbose=params.verbose)
 
     unique_kmers_ind, dist_edges = filter_dist_tuples(dist_cnt, min_coverage=params.min_coverage)
+    stamp.append(("dist_graph_filter_sort_d2h", time.perf_counter()))
 
     output_results(kmer_index=kmer_index, min_coverage=params.min_coverage,
                    unique_kmers_ind=unique_kmers_ind, dist_edges=dist_edges, outdir=params.outdir)
+    stamp.append(("write_files", time.perf_counter()))
+    LAST_TIMINGS.clear()
+    LAST_TIMINGS.update({name: t - stamp[i][1] for i, (name, t) in enumerate(stamp[1:])})
+    LAST_TIMINGS["total"] = stamp[-1][1] - stamp[0][1]
 
 
 if __name__ == "__main__":

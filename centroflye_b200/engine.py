@@ -406,19 +406,20 @@ class Engine:
         t = self.torch
         return t.stack([counters[0], counters[1], cursors.max().to(t.int64)])
 
-    def docfreq_stream(self, reads, k, band=None, with_counts=False, want_table=False):
+    def docfreq_stream(self, reads, k, band=None, with_counts=False, want_table=False, table_buf=None):
         """Two-phase stage A on one GPU -> (rare, table) or None when phase 2 could not hold a partition (more than
         65535 reads sharing a k-mer, or a partition that does not fit after 64-fold splitting): the caller falls back
         to the single-kernel form.  rare = unordered keys inside band = (lo, hi, max_nonuniq) (a tuple with the two
         count tensors when with_counts); table = the dense DocFreqTable when want_table.  One host sync at the end
-        (two when the table is wanted: its size comes from phase 1)."""
+        (two when the table is wanted and no table_buf -- int64[2 * slots], at least one slot per k-mer occurrence --
+        is given: its size then comes from phase 1)."""
         t = self.torch
         total_k = max(reads.n_bases - reads.n_reads * (k - 1), 0)
         n_parts, part_cap = self.stream_plan(total_k, reads.n_reads)
         for attempt in range(3):
             records, cursors, ecounters = self.emit_records(reads, k, n_parts, part_cap)
-            dense = None
-            if want_table:
+            dense = table_buf if want_table else None
+            if want_table and dense is None:
                 n_rec = int(cursors.clamp(max=part_cap).sum(dtype=t.int64).item())  # distinct k-mers <= records
                 dense = self._empty(2 * max(n_rec, 1), t.int64)
             out = self.finish_count(lambda counters: self.count_records(records, cursors, n_parts, part_cap, k, band,
@@ -434,7 +435,7 @@ class Engine:
             self.part_cap_seen[n_parts] = max(self.part_cap_seen.get(n_parts, 0), biggest)
             if not (isinstance(rare, str) and rare == "emit-overflow"):
                 break
-            del records, dense  # a partition buffer was too small: once more with the size phase 1 measured
+            del records  # a partition buffer was too small: once more with the size phase 1 measured
             part_cap = int(biggest * 1.05) + 256
         else:
             raise CfkError("stage A: partition buffers overflowed three times (internal error)")

@@ -21,6 +21,8 @@ aligner, neither of which is available.  This module owns the rest:
 """
 from dataclasses import dataclass
 
+import os
+
 import numpy as np
 
 from .encode import ascii_to_codes, codes_to_ascii
@@ -70,6 +72,20 @@ def simulate_genome(unit, multiplicity, div_rate, seed, flank_len=200000):
     left = rng.integers(0, 4, size=flank_len, dtype=np.uint8)
     right = rng.integers(0, 4, size=flank_len, dtype=np.uint8)
     return np.concatenate([left, arr, right]), flank_len, arr.size
+
+
+GENOME_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "genomes")
+
+
+def load_genome(name):
+    """A genome made by the reference's own simulate_tandem_repeat.py (oracle/make_genomes.py wrote it 2-bit packed
+    under tests/golden/genomes/) -> (flanked genome codes, array start, array length, unit string)."""
+    d = np.load(os.path.join(GENOME_DIR, name + ".npz"))
+    packed, n = d["packed"], int(d["n"])
+    codes = np.empty(packed.size * 4, dtype=np.uint8)
+    for j in range(4):
+        codes[j::4] = (packed >> (2 * j)) & 3
+    return codes[:n], int(d["array_start"]), int(d["array_len"]), str(d["unit"])
 
 
 @dataclass

@@ -31,6 +31,9 @@ OUT = os.path.join(ROOT, "tests", "golden", "genomes")
 GENOMES = {
     # configs[0] / configs[1] / configs[3]: the cenX-like array
     "cenx_dxz1_m1500_s1": dict(unit="supplementary_data/DXZ1_rc.fasta", multiplicity=1500, div_rate=0.01, seed=1),
+    # weak scaling of configs[1] over N GPUs (bench.py --gpus N): N cenX-like arrays, array j from seed 1 + j
+    **{f"cenx_dxz1_m1500_s{s}": dict(unit="supplementary_data/DXZ1_rc.fasta", multiplicity=1500, div_rate=0.01, seed=s)
+       for s in range(2, 9)},
     # configs[2]: the cen6-like array
     "cen6_d6z1_m1000_s4": dict(unit="supplementary_data/D6Z1.fasta", multiplicity=1000, div_rate=0.01, seed=4),
 }
@@ -46,6 +49,8 @@ def main():
     from centroflye_b200.encode import ascii_to_codes
     os.makedirs(OUT, exist_ok=True)
     for name, g in GENOMES.items():
+        if os.path.exists(os.path.join(OUT, name + ".npz")) and "--force" not in sys.argv:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             argv = ["simulate_tandem_repeat.py", "--unit", os.path.join(REF, g["unit"]), "--multiplicity",
                     str(g["multiplicity"]), "--div-rate", str(g["div_rate"]), "--seed", str(g["seed"]), "-o", tmp]
