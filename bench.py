@@ -22,6 +22,8 @@ host-resident results (D2H inside); `e2e_cli` is the drop-in command line from a
 files.  --scale shrinks the array multiplicity (parity / smoke use); 1.0 is the configuration the metric is quoted on.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -511,7 +513,8 @@ def e2e_cli(report_fn, tmp, P, n_bases):
     best = None
     for _ in range(2):  # the second call has warm allocator pools and file cache, like the second read of a pipeline
         t = time.perf_counter()
-        dbkr.main(argv)
+        with contextlib.redirect_stdout(io.StringIO()):  # the command line is verbose by default, like the reference's
+            dbkr.main(argv)
         dt = time.perf_counter() - t
         if best is None or dt < best[0]:
             best = (dt, dict(dbkr.LAST_TIMINGS))
