@@ -249,7 +249,10 @@ class ShardedRecruiter:
         on_clouds(index, csr) is called as soon as the rare set and this rank's clouds are final."""
         from .engine import DistResult
         eng, t = self.eng, self.torch
-        rare = self.global_rare_stream(lo, hi, max_nonuniq) if eng.docfreq_mode == "stream" else None
+        if lo > hi or max_nonuniq < 0:  # dbkr.py:57-62 deletes every k-mer when max_nonuniq < 0; an empty band holds none
+            rare = eng._empty(0, t.int64)[:0]
+        else:
+            rare = self.global_rare_stream(lo, hi, max_nonuniq) if eng.docfreq_mode == "stream" else None
         if rare is None:
             table = eng._count_docfreq_direct(self.reads, self.k)  # hashed table: this exchange looks keys up
             with eng._stage("exchange_docfreq"):

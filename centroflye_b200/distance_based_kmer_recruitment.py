@@ -89,9 +89,25 @@ class KmerFreqs(Mapping):
 
 
 class RareKmerSet(set):
-    """``set[str]`` of rare k-mers that remembers its sorted device copy (ids = ranks)."""
+    """``set[str]`` of rare k-mers that remembers its sorted device copy (ids = ranks).  Any in-place change of the
+    set drops the device copy: the next consumer rebuilds it from the strings."""
     _cfk_index = None
     _cfk_k = None
+
+
+def _dropping_index(name):
+    method = getattr(set, name)
+
+    def mutate(self, *args, **kwargs):
+        self._cfk_index = None
+        return method(self, *args, **kwargs)
+    mutate.__name__ = name
+    return mutate
+
+
+for _name in ("add", "discard", "remove", "pop", "clear", "update", "difference_update", "intersection_update",
+              "symmetric_difference_update", "__ior__", "__iand__", "__isub__", "__ixor__"):
+    setattr(RareKmerSet, _name, _dropping_index(_name))
 
 
 class KmerRanks(Mapping):

@@ -121,7 +121,13 @@ class Engine:
 
     # ---- plumbing ---------------------------------------------------------------------------
     def _stream(self):
-        return self.torch.cuda.current_stream(self.device).cuda_stream
+        """The stream every C-ABI call of this engine is enqueued on.  The library launches on the CURRENT device, so
+        an engine bound to another GPU of the same process makes its device current first (a side effect the caller
+        sees; one process per GPU never pays for it)."""
+        t = self.torch
+        if t.cuda.current_device() != self.device.index:
+            t.cuda.set_device(self.device)
+        return t.cuda.current_stream(self.device).cuda_stream
 
     def _to_dev(self, arr, dtype=None):
         t = self.torch.from_numpy(np.ascontiguousarray(arr))

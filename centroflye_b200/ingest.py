@@ -19,6 +19,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from .encode import READ_ALIGN_BASES, ascii_to_codes, pack_codes
+from .ncrf_parser import motif_unit_columns
 
 _GAP = ord("-")
 
@@ -106,7 +107,9 @@ def units_from_report(report, batch, n=1):
     boundaries = []
     for r_id in batch.r_ids:
         rec = report.records[r_id]
-        coords = rec.unit_columns(n=n)
+        # any record with the reference's attributes will do (a report parsed by the reference's own ncrf_parser.py,
+        # read_placer.py:9,106-114): the segmentation is a free function, not a method of this repo's record class
+        coords = motif_unit_columns(rec.m_al, len(rec.r_al), rec.motif, n=n)
         if not coords:
             boundaries.append(np.empty(0, dtype=np.int64))
             continue

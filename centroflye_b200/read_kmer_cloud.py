@@ -132,6 +132,12 @@ def _native(report, n):
         return None  # the Python path below raises the reference-shaped error, if any
     if batch.r_ids != list(report.records.keys()):
         return None
+    # a caller may have edited records in place since the file was parsed: the file is only trusted while every
+    # record still has the gap-free length the file gave it (C-level scans; the bases themselves are not compared)
+    for r_id, n_bases in zip(batch.r_ids, batch.read_len.tolist()):
+        r_al = report.records[r_id].r_al
+        if len(r_al) - r_al.count("-") != n_bases:
+            return None
     return batch, units
 
 
@@ -268,3 +274,16 @@ def filter_reads_kmer_clouds(kmer_clouds, min_mult=2, max_mult=math.inf):
         for pos, kept in enumerate(new_state.read_sets(r)):
             kmer_clouds[r_id].kmers[pos] = kept
     return kmer_clouds
+
+
+def get_all_kmers(kmer_clouds):
+    """read_kmer_cloud.py:57-63 AS WRITTEN: the loop reads ``kmer_clouds.all_kmers`` -- an attribute of the dict, not
+    of the cloud it iterates over -- so a non-empty argument raises AttributeError and an empty one returns [].
+    Nothing in the reference calls it; it is here so that ``from read_kmer_cloud import *`` binds the same names with
+    the same behaviour."""
+    merged = []
+    for _ in kmer_clouds:
+        merged += kmer_clouds.all_kmers
+    merged.sort()
+    assert len(set(merged)) == len(merged)
+    return merged

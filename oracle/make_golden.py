@@ -46,7 +46,8 @@ CASES = {
         flank_len=3000, coverage=14, error_rate=0.06, read_seed=2, median_len=9000, sigma=0.4,
         min_len=5200, max_len=30000,
         points=[dict(k=19, coverage=14), dict(k=19, coverage=14, max_nonuniq=0, min_coverage=2),
-                dict(k=15, coverage=14, bottom=0.5, top=2.0), dict(k=27, coverage=10, min_coverage=3)],
+                dict(k=15, coverage=14, bottom=0.5, top=2.0), dict(k=27, coverage=10, min_coverage=3),
+                dict(k=19, coverage=14, min_coverage=8), dict(k=19, coverage=14, max_nonuniq=0)],
     ),
     "rand311": dict(
         unit_random=(311, 7), multiplicity=50, div_rate=0.02, genome_seed=3,
@@ -79,6 +80,21 @@ def _ref():
         import simulate_tandem_repeat
         from utils.bio import read_bio_seq
     return dbkr, ncrf_parser, read_kmer_cloud, simulate_tandem_repeat, read_bio_seq
+
+
+NEW_ONLY = False  # --new-only: keep the fixtures that exist, add the missing ones
+
+
+def _ref_get_kmer_counts_reads():
+    """get_kmer_counts_reads compiled from its own source lines in the reference file (nothing else of the module)."""
+    import ast
+    path = os.path.join(REF, "scripts", "better_consensus_unit_reconstruction.py")
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_kmer_counts_reads")
+    ns = {}
+    exec(compile(ast.Module(body=[ast.parse("from collections import defaultdict").body[0], fn], type_ignores=[]),
+                 path, "exec"), ns)
+    return ns["get_kmer_counts_reads"]
 
 
 def _dump(path, obj):
@@ -156,7 +172,20 @@ def build_case(name, spec, outdir):
            "discarded": sorted(report.discarded_reads),
            "classify_3000": [sorted(x) for x in report.classify(large_threshold=3000)]})
 
+    for k_count in (19, 30):  # total-occurrence counts of the reference's get_kmer_counts_reads (row f3)
+        fn = os.path.join(outdir, f"kmer_counts_k{k_count}.json")
+        if not (NEW_ONLY and os.path.exists(fn)):
+            counts = _ref_get_kmer_counts_reads()(report, k=k_count)
+            lines = "".join(f"{kmer} {c}\n" for kmer, c in sorted(counts.items()))
+            with open(fn, "w") as f:
+                json.dump({"k": k_count, "n_distinct": len(counts), "n_total": int(sum(counts.values())),
+                           "max_count": int(max(counts.values())), "sorted_lines_md5": hashlib.md5(lines.encode()).hexdigest(),
+                           "source": "scripts/better_consensus_unit_reconstruction.py:127-135, the function's own source "
+                                     "compiled out of the reference file (the module imports edlib, absent here)"},
+                          f, indent=1, sort_keys=True)
     for pi, point in enumerate(spec["points"]):
+        if NEW_ONLY and os.path.exists(os.path.join(outdir, f"p{pi}.json")):
+            continue
         p = dict(DEFAULTS)
         p.update(point)
         k = p["k"]
@@ -219,7 +248,9 @@ def build_case(name, spec, outdir):
 
 
 def main():
-    names = sys.argv[1:] or list(CASES)
+    global NEW_ONLY
+    NEW_ONLY = "--new-only" in sys.argv
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(CASES)
     for name in names:
         build_case(name, CASES[name], os.path.join(ROOT, "tests", "golden", name))
 

@@ -85,3 +85,30 @@ def test_full_size_alternative_kernels_agree(full):
     got = res.edges.cpu().numpy().view(np.uint32).reshape(-1, 4)
     ref = full["res"].edges.cpu().numpy().view(np.uint32).reshape(-1, 4)
     assert np.array_equal(_canon(got), _canon(ref))
+
+
+def test_cen6_noisy_reads_match_oracle():
+    """BASELINE.json configs[2] (D6Z1 unit of 3222 bp from the reference simulator, 12 % read errors,
+    --kmer-survival-rate 0.09 --coverage 50) on one GPU at 0.3 of the array (300 copies, 5e7 read bases): far more
+    one-off k-mers per read than configs[1] and a different band.  The sharded form of the same instance is
+    tests/test_gpu_parity.py::test_sharded_recruitment_two_gpus / bench.py --config cen6 --gpus N (parity leg)."""
+    import bench
+    from centroflye_b200.engine import default_engine
+    from oracle import c_oracle
+    eng = default_engine()
+    unit, batch, units = bench.simulate("cen6", 0.3)
+    P = bench.CONFIGS["cen6"]["params"]
+    lo, hi = bench.band(P)
+    k = P["k"]
+    index, csr, res = eng.recruit(eng.upload_reads(batch, k), eng.upload_units(units, k), k, lo, hi, P["max_nonuniq"],
+                                  P["min_d"], P["max_d"], P["min_coverage"])
+    assert getattr(eng, "stream_fallbacks", 0) == 0
+    want = c_oracle.recruit(batch, units, k, lo, hi, P["max_nonuniq"], P["min_d"], P["max_d"], P["min_coverage"],
+                            threads=os.cpu_count() or 1)
+    assert np.array_equal(index.sorted_keys.cpu().numpy().view(np.uint64), want["rare"])
+    assert np.array_equal(csr.unit_ptr.cpu().numpy()[: units.n_units + 1], want["unit_ptr"])
+    assert np.array_equal(csr.ids.cpu().numpy().view(np.uint32), want["ids"])
+    assert res.n_increments == want["n_increments"]
+    got = res.edges.cpu().numpy().view(np.uint32).reshape(-1, 4)
+    assert np.array_equal(_canon(got), _canon(want["edges"]))
+    assert np.array_equal(np.sort(res.selected.cpu().numpy().view(np.uint32)), want["selected"])

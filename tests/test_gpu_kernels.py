@@ -320,3 +320,81 @@ def test_docfreq_claim_races(eng, docfreq_mode, seed):
     assert np.array_equal(keys[order], wk)
     assert np.array_equal(nr.cpu().numpy().view(np.uint32)[order], wr)
     assert np.array_equal(nm.cpu().numpy().view(np.uint32)[order], wm)
+
+
+def test_stream_count_splits_oversized_partitions(eng):
+    """Phase 2 of the two-phase stage A plans a partition for cfk_docfreq_part_target() k-mer occurrences but its
+    block's table holds fewer distinct k-mers: reads without repeats (every k-mer new) overflow it, and the kernel must
+    take the partition again by halves of its hash range -- same counts, no fall-back to the single-kernel form."""
+    from centroflye_b200.ingest import pack_reads
+    from oracle import c_oracle
+    rng = np.random.default_rng(5)
+    codes = [rng.integers(0, 4, size=int(rng.integers(20000, 60000)), dtype=np.uint8) for _ in range(60)]
+    codes += [codes[3][1000:30000].copy(), codes[7].copy()]  # two reads sharing long stretches with others
+    batch = pack_reads(codes, [f"r{i}" for i in range(len(codes))])
+    k = 21
+    assert int(eng.lib.cfk_docfreq_part_target()) > int(eng.lib.cfk_docfreq_part_distinct())
+    old, eng.docfreq_mode = eng.docfreq_mode, "stream"
+    old_group = eng.stream_group
+    try:
+        for group in (1, 8):  # grouped units that do not fit are retried partition by partition, then split
+            eng.stream_group = group
+            before = getattr(eng, "stream_fallbacks", 0)
+            table = eng.count_docfreq(eng.upload_reads(batch, k), k)
+            assert table.dense and getattr(eng, "stream_fallbacks", 0) == before
+            keys, nr, nm = eng.table_select(table, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)
+            keys = keys.cpu().numpy().view(np.uint64)
+            order = np.argsort(keys)
+            wk, wr, wm = c_oracle.docfreq(c_oracle.unpacked_codes(batch), batch, k)
+            assert np.array_equal(keys[order], wk)
+            assert np.array_equal(nr.cpu().numpy().view(np.uint32)[order], wr)
+            assert np.array_equal(nm.cpu().numpy().view(np.uint32)[order], wm)
+    finally:
+        eng.docfreq_mode, eng.stream_group = old, old_group
+
+
+def test_stream_partition_buffers_grow(eng):
+    """A k-mer present in every read adds one record per read to ONE partition: with a deliberately small first guess
+    the buffers overflow, phase 1 reports the size it needed and the call repeats itself with it."""
+    from centroflye_b200.ingest import pack_reads
+    from oracle import c_oracle
+    rng = np.random.default_rng(9)
+    shared = rng.integers(0, 4, size=400, dtype=np.uint8)
+    codes = [np.concatenate([rng.integers(0, 4, size=5200, dtype=np.uint8), shared,
+                             rng.integers(0, 4, size=300, dtype=np.uint8)]) for _ in range(700)]
+    batch = pack_reads(codes, [f"r{i}" for i in range(len(codes))])
+    k = 19
+    old = (eng.docfreq_mode, eng.part_slack, dict(eng.part_cap_seen))
+    eng.docfreq_mode, eng.part_slack = "stream", 0.2
+    eng.part_cap_seen.clear()
+    plan = eng.stream_plan
+    eng.stream_plan = lambda *a, **kw: (plan(*a, **kw)[0], 64)  # 64 records per partition buffer: far too few
+    try:
+        rare = eng.rare_kmers(eng.upload_reads(batch, k), k, 600, 700, 3)
+        assert max(eng.part_cap_seen.values()) > 64  # the measured size was remembered
+        wk, wr, wm = c_oracle.docfreq(c_oracle.unpacked_codes(batch), batch, k)
+        want = wk[(wr >= 600) & (wr <= 700) & (wm <= 3)]
+        assert want.size >= 400 - k
+        assert np.array_equal(np.sort(rare.cpu().numpy().view(np.uint64)), want)
+    finally:
+        eng.stream_plan = plan
+        eng.docfreq_mode, eng.part_slack = old[0], old[1]
+        eng.part_cap_seen.clear()
+        eng.part_cap_seen.update(old[2])
+
+
+def test_negative_max_nonuniq_selects_nothing(eng):
+    """dbkr.py:57-62: with max_nonuniq < 0 the test `non_unique_freqs[kmer] <= max_nonuniq` fails for every k-mer, so
+    all_kmers ends empty and so does the rare set (the u32 conversion must not turn -1 into "everything")."""
+    from centroflye_b200.ingest import pack_reads
+    rng = np.random.default_rng(2)
+    codes = [_repetitive_read(rng, 9000, 300, 0.03) for _ in range(12)]
+    batch = pack_reads(codes, [f"r{i}" for i in range(len(codes))])
+    for mode in ("stream", "resident"):
+        old, eng.docfreq_mode = eng.docfreq_mode, mode
+        try:
+            assert eng.rare_kmers(eng.upload_reads(batch, 15), 15, 1, 100, -1).numel() == 0
+            assert eng.rare_kmers(eng.upload_reads(batch, 15), 15, 5, 4, 3).numel() == 0  # empty band
+            assert eng.rare_kmers(eng.upload_reads(batch, 15), 15, 1, 100, 3).numel() > 0
+        finally:
+            eng.docfreq_mode = old

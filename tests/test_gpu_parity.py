@@ -241,18 +241,27 @@ def test_sharded_recruitment_two_gpus():
 
 @pytest.mark.parametrize("case", golden_cases())
 @pytest.mark.parametrize("k", [19, 30])
-def test_total_kmer_counts_match_reference_loop(golden, mods, case, k):
-    """get_kmer_counts_reads (better_consensus_unit_reconstruction.py:127-135, restated: every k-mer occurrence of every
-    gap-free read row counts) on the device."""
+def test_total_kmer_counts_match_reference(golden, mods, case, k):
+    """get_kmer_counts_reads on the device against the golden made by the reference's own function
+    (better_consensus_unit_reconstruction.py:127-135, oracle/make_golden.py): distinct k-mers, total, largest count and
+    the md5 of the sorted "kmer count" lines -- and against the loop restated here, entry by entry."""
+    import hashlib
+    import json
+    import os
     from collections import Counter
     from centroflye_b200.better_consensus_unit_reconstruction import get_kmer_counts_reads
     _, _, NCRF_Report = mods
     rep = NCRF_Report(golden(case).report_path)
+    got = get_kmer_counts_reads(rep, k=k)
+    with open(os.path.join(os.path.dirname(golden(case).report_path), f"kmer_counts_k{k}.json")) as f:
+        gold = json.load(f)
+    items = dict(got.items())
+    assert len(items) == gold["n_distinct"] and sum(items.values()) == gold["n_total"] and max(items.values()) == gold["max_count"]
+    lines = "".join(f"{kmer} {c}\n" for kmer, c in sorted(items.items()))
+    assert hashlib.md5(lines.encode()).hexdigest() == gold["sorted_lines_md5"]
     want = Counter()
     for rec in rep.records.values():
         s = rec.r_al.replace("-", "")
         want.update(s[i:i + k] for i in range(len(s) - k + 1))
-    got = get_kmer_counts_reads(rep, k=k)
-    assert len(got) == len(want)
-    assert dict(got.items()) == dict(want)
+    assert items == dict(want)
     assert got["A" * k] == want.get("A" * k, 0) and got["not a kmer"] == 0

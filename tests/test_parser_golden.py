@@ -64,3 +64,22 @@ def test_segmentation_self_periodic_motif_is_leftmost_match():
 
 def test_rc_passes_unknown_symbols():
     assert RC("ACGTacgt-N") == "N-acgtACGT"
+
+
+def test_units_from_report_takes_reference_style_records(golden):
+    """a report parsed by the REFERENCE's ncrf_parser.py (read_placer.py:9,106-114 keeps it when only the
+    two hot-path modules are swapped) reaches the device path as plain objects with the reference's attributes -- no
+    unit_columns method, no _cfk_source.  The segmentation must not depend on this repo's record class."""
+    import types
+    import numpy as np
+    from centroflye_b200.ingest import batch_from_report, units_from_report
+    rep = NCRF_Report(golden(golden_cases()[0]).report_path)
+    duck = types.SimpleNamespace(records={
+        r_id: types.SimpleNamespace(r_id=r.r_id, r_al=r.r_al, m_al=r.m_al, motif=r.motif, strand=r.strand,
+                                    r_len=r.r_len, r_st=r.r_st, r_en=r.r_en)
+        for r_id, r in rep.records.items()})
+    for n in (1, 2):
+        want = units_from_report(rep, batch_from_report(rep), n=n)
+        got = units_from_report(duck, batch_from_report(duck), n=n)
+        assert np.array_equal(got.read_unit_ptr, want.read_unit_ptr)
+        assert np.array_equal(got.unit_off, want.unit_off) and np.array_equal(got.unit_len, want.unit_len)
