@@ -34,6 +34,7 @@ SIGNATURES = {
                                        _i64, _p, _i32, _p]),
     "cfk_kmer_count_tile": (_int, []),
     "cfk_kmer_count_total": (_int, [_p, _p, _p, _p, _p, _i64, _int, _p, _i64, _p, _p]),
+    "cfk_kmer_count_canonical": (_int, [_p, _p, _p, _p, _p, _i64, _int, _p, _i64, _p, _p]),
     "cfk_table_merge": (_int, [_p, _p, _p, _i64, _p, _i64, _p, _p]),
     "cfk_table_select": (_int, [_p, _i64, _u32, _u32, _u32, _i32, _i32, _p, _p, _p, _i64, _p, _p]),
     "cfk_table_lookup": (_int, [_p, _i64, _p, _i64, _p, _p, _p]),

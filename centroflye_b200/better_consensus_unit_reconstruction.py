@@ -18,3 +18,16 @@ def get_kmer_counts_reads(ncrf_report, k=19):
     table = engine.count_total(reads, batch, k)
     keys, counts, _ = engine.table_select(table, 0, U32_MAX, U32_MAX, with_counts=True)
     return KmerFreqs(to_host_u64(keys), to_host_u32(counts), k, table=table, engine=engine)
+
+
+def get_canonical_kmer_counts(ncrf_report, k=19):
+    """kmer -> occurrences over the gap-free rows of all records with the two strands of a k-mer merged: the count of
+    `jellyfish count -m k -C` that tandemQUAST's select_kmers.py:131-133 dumps for the reads, keyed by the canonical
+    (smaller) strand."""
+    k = check_k(k)
+    engine = default_engine()
+    batch = report_batch(ncrf_report)
+    reads = report_device_reads(ncrf_report, engine, k)
+    table = engine.count_total(reads, batch, k, canonical=True)
+    keys, counts, _ = engine.table_select(table, 0, U32_MAX, U32_MAX, with_counts=True)
+    return KmerFreqs(to_host_u64(keys), to_host_u32(counts), k, table=table, engine=engine)

@@ -472,6 +472,14 @@ constexpr int KC_THREADS = 256;
 constexpr int KC_PER_THREAD = 8;
 constexpr int KC_TILE = KC_THREADS * KC_PER_THREAD;
 
+// reverse complement of a k-mer key (first base most significant; A=0 C=1 G=2 T=3, so the complement is 3 - code)
+__device__ __forceinline__ uint64_t kmer_revcomp(uint64_t kmer, int k) {
+  uint64_t r = __brevll(~kmer);  // complement, then reverse the bit order ...
+  r = ((r & 0xAAAAAAAAAAAAAAAAull) >> 1) | ((r & 0x5555555555555555ull) << 1);  // ... and restore the order inside each base
+  return r >> (64 - 2 * k);
+}
+
+template <bool CANONICAL>
 __global__ void __launch_bounds__(KC_THREADS)
 kmer_count_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ read_off, const int64_t* __restrict__ read_len,
                   const int32_t* __restrict__ tile_read, const int64_t* __restrict__ tile_start, int k, uint64_t* table,
@@ -501,7 +509,9 @@ kmer_count_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict
     kmer = ((kmer << 2) | (win_lo & 3u)) & mask;
     win_lo = (win_lo >> 2) | ((uint64_t)win_hi << 62);
     win_hi >>= 2;
-    const int64_t slot = slot_upsert(table, cap, kmer, home_slot(mix64(kmer), cap));
+    uint64_t key = kmer;
+    if (CANONICAL) key = min(kmer, kmer_revcomp(kmer, k));  // the smaller of the two strands, like `jellyfish count -C`
+    const int64_t slot = slot_upsert(table, cap, key, home_slot(mix64(key), cap));
     if (slot < 0) counters[0] = 1;
     else atomicAdd(reinterpret_cast<uint32_t*>(table + 2 * slot + 1), 1u);
   }
@@ -2392,8 +2402,20 @@ int cfk_kmer_count_total(const uint32_t* packed, const int64_t* read_off, const 
   if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_kmer_count_total: k must be in [1, 31]");
   if (cap < 1 || n_tiles < 0 || n_tiles >= (1ll << 31)) return fail(CFK_ERR_INVALID, "cfk_kmer_count_total: bad sizes");
   if (n_tiles == 0) return CFK_OK;
-  kmer_count_kernel<<<(unsigned)n_tiles, KC_THREADS, 0, (cudaStream_t)stream>>>(packed, read_off, read_len, tile_read, tile_start, k,
-                                                                              table, cap, counters);
+  kmer_count_kernel<false><<<(unsigned)n_tiles, KC_THREADS, 0, (cudaStream_t)stream>>>(packed, read_off, read_len, tile_read,
+                                                                                     tile_start, k, table, cap, counters);
+  CFK_CHECK_LAUNCH("kmer_count_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_kmer_count_canonical(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* tile_read,
+                             const int64_t* tile_start, int64_t n_tiles, int k, uint64_t* table, int64_t cap,
+                             int64_t* counters, cfk_stream_t stream) {
+  if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_kmer_count_canonical: k must be in [1, 31]");
+  if (cap < 1 || n_tiles < 0 || n_tiles >= (1ll << 31)) return fail(CFK_ERR_INVALID, "cfk_kmer_count_canonical: bad sizes");
+  if (n_tiles == 0) return CFK_OK;
+  kmer_count_kernel<true><<<(unsigned)n_tiles, KC_THREADS, 0, (cudaStream_t)stream>>>(packed, read_off, read_len, tile_read,
+                                                                                    tile_start, k, table, cap, counters);
   CFK_CHECK_LAUNCH("kmer_count_kernel", 1);
   return CFK_OK;
 }

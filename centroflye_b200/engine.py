@@ -452,9 +452,10 @@ class Engine:
             table = DocFreqTable(slots=dense[:2 * n], cap=n, dense=True)
         return rare, table
 
-    def count_total(self, reads, batch, k):
+    def count_total(self, reads, batch, k, canonical=False):
         """Total occurrences of every k-mer over all reads (no per-read de-duplication) -> DocFreqTable whose n_reads
-        field holds the count (better_consensus_unit_reconstruction.py:127-135)."""
+        field holds the count (better_consensus_unit_reconstruction.py:127-135).  canonical=True merges the two strands
+        of a k-mer (`jellyfish count -C`, ext/tandemQUAST/scripts/select_kmers.py:131-133)."""
         k = check_k(k)
         tile = int(self.lib.cfk_kmer_count_tile())
         nk = np.maximum(batch.read_len - k + 1, 0)
@@ -467,7 +468,8 @@ class Engine:
         while True:
             table = self.new_table(cap)
             counters = self._counters()
-            _lib.call("cfk_kmer_count_total", self._p(reads.packed), self._p(reads.read_off), self._p(reads.read_len),
+            _lib.call("cfk_kmer_count_canonical" if canonical else "cfk_kmer_count_total", self._p(reads.packed),
+                      self._p(reads.read_off), self._p(reads.read_len),
                       self._p(d_read), self._p(d_start), int(tile_read.size), k, self._p(table.slots), cap,
                       self._p(counters), self._stream())
             if int(counters.cpu()[0]) == 0:

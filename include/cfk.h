@@ -159,6 +159,13 @@ int cfk_kmer_count_total(const uint32_t* packed, const int64_t* read_off, const 
                          const int64_t* tile_start, int64_t n_tiles, int k, uint64_t* table, int64_t cap, int64_t* counters,
                          cfk_stream_t stream);
 
+/* The same count with the two strands of a k-mer merged (second half): what tandemQUAST gets from
+ * `jellyfish count -m K -C` on the reads, scripts/ext/tandemQUAST/scripts/select_kmers.py:131-133 -- every k-mer
+ * occurrence adds 1 to its CANONICAL form, the smaller of the k-mer and its reverse complement (A < C < G < T). */
+int cfk_kmer_count_canonical(const uint32_t* packed, const int64_t* read_off, const int64_t* read_len, const int32_t* tile_read,
+                             const int64_t* tile_start, int64_t n_tiles, int k, uint64_t* table, int64_t cap,
+                             int64_t* counters, cfk_stream_t stream);
+
 /* Merge (key, n_reads, n_multi) records counted elsewhere (another GPU's shard) into a table:
  * the owner-side half of the multi-GPU all-to-all.  counters[0] != 0: full. */
 int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n, uint64_t* table,

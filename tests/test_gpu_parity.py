@@ -265,3 +265,26 @@ def test_total_kmer_counts_match_reference(golden, mods, case, k):
         want.update(s[i:i + k] for i in range(len(s) - k + 1))
     assert items == dict(want)
     assert got["A" * k] == want.get("A" * k, 0) and got["not a kmer"] == 0
+
+
+@pytest.mark.parametrize("case", golden_cases())
+@pytest.mark.parametrize("k", [19, 31])
+def test_canonical_kmer_counts(golden, mods, case, k):
+    """`jellyfish count -C` semantics (ext/tandemQUAST/scripts/select_kmers.py:131-133; the binary is an external
+    dependency absent from the reference tree, so its published rule is restated): every k-mer occurrence counts for
+    the smaller of the k-mer and its reverse complement (scripts/utils/bio.py:27-29 is the reference's RC)."""
+    from collections import Counter
+    from centroflye_b200.better_consensus_unit_reconstruction import get_canonical_kmer_counts, get_kmer_counts_reads
+    _, _, NCRF_Report = mods
+    rep = NCRF_Report(golden(case).report_path)
+    comp = str.maketrans("ACGT", "TGCA")
+    want = Counter()
+    for rec in rep.records.values():
+        s = rec.r_al.replace("-", "")
+        for i in range(len(s) - k + 1):
+            kmer = s[i:i + k]
+            want[min(kmer, kmer.translate(comp)[::-1])] += 1
+    got = dict(get_canonical_kmer_counts(rep, k=k).items())
+    assert got == dict(want)
+    if k == 19:  # merging strands conserves the total
+        assert sum(got.values()) == sum(dict(get_kmer_counts_reads(rep, k=k).items()).values())
