@@ -253,7 +253,7 @@ def test_total_kmer_counts_match_reference(golden, mods, case, k):
     _, _, NCRF_Report = mods
     rep = NCRF_Report(golden(case).report_path)
     got = get_kmer_counts_reads(rep, k=k)
-    with open(os.path.join(os.path.dirname(golden(case).report_path), f"kmer_counts_k{k}.json")) as f:
+    with open(os.path.join(golden(case).dir, f"kmer_counts_k{k}.json")) as f:
         gold = json.load(f)
     items = dict(got.items())
     assert len(items) == gold["n_distinct"] and sum(items.values()) == gold["n_total"] and max(items.values()) == gold["max_count"]
