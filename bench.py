@@ -9,8 +9,11 @@ Workloads (config.workload), all drawn from genomes made by the reference's own 
   cenx    BASELINE.json configs[1] (the default, the configuration the metric is quoted on): DXZ1 x 1500 (3.08 Mb array,
           seed 1) at 50x long reads with 6 % errors, k = 19, --coverage 32; one step = the whole recruitment path
           (document frequency -> rare band -> per-unit clouds -> unit-distance pair graph -> edge filter).  At N GPUs
-          (weak scaling) the read set is that of N such arrays (genome seeds 1..N, read seeds 3..3+N-1), every rank
-          holding the reads i = rank mod N of every array; counts, rare set and distance graph stay global.
+          (weak scaling) the read set is that of N such arrays -- array j >= 2 from the reference simulator too, on its
+          own unit (DXZ1 with 30 % of the bases substituted: arrays of ONE unit share their error k-mers, which at
+          N x 50x enter the rare band and nearly double the pair increments per array, so the work per GPU would not be
+          fixed) -- every rank holding the reads i = rank mod N of every array; counts, rare set and distance graph
+          stay global.
   cen6    configs[2]: D6Z1 x 1000 (3.2 Mb, seed 4), 50x, 12 % errors, --kmer-survival-rate 0.09 --coverage 50; the ONE
           read set sharded over the N ranks (strong scaling).
   stream  configs[4]: a stream of independent 155-Mbase batches drawn like configs[1] (batch b = read seed 3 + b, batch 0
@@ -40,7 +43,8 @@ sys.path.insert(0, ROOT)
 CONFIGS = {
     "cenx": dict(params=dict(k=19, coverage=32, min_coverage=4, min_d=1, max_d=150, bottom=0.9, top=3.0,
                              kmer_survival_rate=0.34, max_nonuniq=3),
-                 data=dict(genome="cenx_dxz1_m1500_s{seed}", genome_seed=1, read_coverage=50, error_rate=0.06, read_seed=3),
+                 data=dict(genome="cenx_dxz1_m1500_s{seed}", genome_more="cenx_like_u{seed}_m1500_s{seed}", genome_seed=1,
+                           read_coverage=50, error_rate=0.06, read_seed=3),
                  label="configs[1]: cenX-like array, reference simulator DXZ1_rc x 1500 (3.08 Mb, div-rate 0.01, seed 1) "
                        "+ 2 x 200 kb flanks, 50x reads, 6% errors, k=19, coverage=32, max_d=150: full recruitment + "
                        "read_kmer_cloud build"),
@@ -73,12 +77,13 @@ def simulate(config, scale, rank=0, world=1, n_arrays=None, read_seed_shift=0, k
     n_arrays = (world if config != "cen6" else 1) if n_arrays is None else n_arrays
     reads, unit = [], None
     for j in range(n_arrays):
-        genome, a0, alen, unit = synth.load_genome(D["genome"].format(seed=D["genome_seed"] + j))
+        genome, a0, alen, unit_j = synth.load_genome((D["genome"] if j == 0 else D["genome_more"]).format(seed=D["genome_seed"] + j))
+        unit = unit or unit_j
         if scale != 1.0:  # fewer copies of the unit: the left flank, the first copies, the right flank
-            keep = max(8, int(round(alen / len(unit) * scale))) * len(unit)
+            keep = max(8, int(round(alen / len(unit_j) * scale))) * len(unit_j)
             genome = np.concatenate([genome[:a0 + keep], genome[a0 + alen:]])
             alen = keep
-        reads += synth.simulate_reads(genome, a0, alen, unit, D["read_coverage"], D["error_rate"],
+        reads += synth.simulate_reads(genome, a0, alen, unit_j, D["read_coverage"], D["error_rate"],
                                       D["read_seed"] + j + read_seed_shift, id_prefix="read" if j == 0 else f"a{j}_read",
                                       shard=(rank, world) if world > 1 else None)
     batch, units = batch_from_synth(reads, len(unit))
@@ -459,7 +464,8 @@ def run_recruit(args):
                     "edges stay with their source's rank")
     workload = C["label"]
     if world > 1:
-        workload += (f"; weak scaling: {world} such arrays (genome seeds 1..{world}), reads of every array dealt to {world} ranks"
+        workload += (f"; weak scaling: {world} such arrays (reference simulator, seeds 1..{world}; arrays 2.. on their own units, "
+                     f"DXZ1 with 30% of the bases substituted), reads of every array dealt to {world} ranks"
                      if args.config == "cenx" else f"; strong scaling: the one read set sharded over {world} ranks")
     line = {
         "metric": "k-mer recruitment read-bases/s", "value": n_bases_total / (ms * 1e-3), "unit": "read-bases/s",

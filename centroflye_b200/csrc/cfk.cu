@@ -1983,6 +1983,7 @@ struct SketchArgs {
   int64_t max_cand;
   int64_t* counters;
   struct SketchChunk* chunk;  // the warp's current chunk of cand[]
+  bool prefetch;              // ask the code blocks of a pass's units into L2 up front (graphs larger than L2)
 };
 
 constexpr int SK_CAND_CHUNK = 256;
@@ -2040,6 +2041,19 @@ struct SketchPre {
   int64_t unit;
 };
 
+// The code blocks of the units a pass is about to walk (one unit per lane) are asked into L2 up front: on one GPU the
+// whole cloud CSR sits in L2 anyway, on N GPUs the all-gathered CSR is N times larger and every window would otherwise
+// wait for DRAM behind a one-window look-ahead.  A block of 128 codes = 256 B = two lines.
+__device__ __forceinline__ void sk_prefetch_unit(const uint2* codes, uint32_t up, uint32_t ue, uint32_t ub) {
+  if (ue <= up) return;
+  const uint32_t n_blocks = (ue - up + (uint32_t)SK_WINDOW - 1u) / (uint32_t)SK_WINDOW;
+  const char* base = reinterpret_cast<const char*>(codes + (size_t)ub * 32u);
+  for (uint32_t b = 0; b < n_blocks && b < 4u; ++b) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b * 256u));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + b * 256u + 128u));
+  }
+}
+
 __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, int64_t lo_id, int64_t hi_id,
                            const SketchPre* pre = nullptr) {
   const int lane = threadIdx.x & 31;
@@ -2055,6 +2069,7 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
     up = pre->up;
     ue = pre->ue;
     ub = (uint32_t)sk_block((int64_t)up, pre->unit);
+    if (A.prefetch) sk_prefetch_unit(A.codes, up, ue, ub);
     rest = __ballot_sync(FULL, ue > up);
     if (rest) {
       src = __ffs(rest) - 1;
@@ -2086,6 +2101,7 @@ __device__ int sketch_pass(uint32_t tbase, const SketchArgs& A, int d0, int nd, 
           ub = (uint32_t)sk_block(p0, u);
         }
       }
+      if (A.prefetch) sk_prefetch_unit(A.codes, up, ue, ub);
       rest = __ballot_sync(FULL, ue > up);
       if (!rest) continue;
       src = __ffs(rest) - 1;
@@ -2264,7 +2280,7 @@ pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restr
                    const uint32_t* __restrict__ perm_ids, const uint32_t* __restrict__ unit_last, const int64_t* __restrict__ occ_ptr,
                    const uint32_t* __restrict__ occ, const uint32_t* __restrict__ occ_last, int64_t n_kmers, int64_t a_begin,
                    int64_t a_end, int32_t a_stride, int32_t min_d, int32_t max_d, uint32_t min_cov, uint4* cand,
-                   int64_t max_cand, int64_t* counters) {
+                   int64_t max_cand, int64_t* counters, int prefetch) {
   extern __shared__ __align__(16) unsigned char pc_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t tbase = (uint32_t)__cvta_generic_to_shared(pc_smem) + (uint32_t)warp * SK_WARP_BYTES;
@@ -2285,7 +2301,7 @@ pair_sketch_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restr
     const int dlim = source_scope(unit_ptr, unit_last, occ_a, m, dmin, max_d, min_cov, incr_total, last_a);
     if (dlim < dmin) continue;
     SketchArgs A{unit_ptr, perm_ids ? perm_ids : ids, perm_ids != nullptr, codes, unit_last, last_a, occ_a, m, n_kmers, a, min_cov - 1u, cand,
-                 max_cand, counters, &chunk};
+                 max_cand, counters, &chunk, prefetch != 0};
     sketch_source(tbase, A, dmin, dlim, splits);
   }
   {
@@ -2691,9 +2707,13 @@ int cfk_pair_sketch(const int64_t* unit_ptr, const uint32_t* ids, const uint16_t
     cudaError_t e = cfk::ensure_dynamic_smem(pair_sketch_kernel, smem, &attr_done);
     if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_pair_sketch: cudaFuncSetAttribute", e);
   }
+  // codes + ids of the graph beyond ~half of the 126 MB L2 (the all-gathered graph of several GPUs): the kernel asks
+  // each pass's code blocks into L2 ahead of its walk (CFK_SKETCH_PREFETCH=0 / 1 forces it off / on)
+  int prefetch = 6 * n_entries > (48ll << 20);
+  if (const char* env = getenv("CFK_SKETCH_PREFETCH")) prefetch = atoi(env) != 0;
   pair_sketch_kernel<<<(unsigned)n_blocks, SK_WARPS * 32, smem, (cudaStream_t)stream>>>(
       unit_ptr, ids, (const uint2*)codes, perm_ids, unit_last, occ_ptr, occ, occ_last, n_kmers, a_begin, a_end, a_stride, min_d, max_d, min_cov, (uint4*)cand,
-      max_cand, counters);
+      max_cand, counters, prefetch);
   CFK_CHECK_LAUNCH("pair_sketch_kernel", 1);
   return CFK_OK;
 }

@@ -31,9 +31,12 @@ OUT = os.path.join(ROOT, "tests", "golden", "genomes")
 GENOMES = {
     # configs[0] / configs[1] / configs[3]: the cenX-like array
     "cenx_dxz1_m1500_s1": dict(unit="supplementary_data/DXZ1_rc.fasta", multiplicity=1500, div_rate=0.01, seed=1),
-    # weak scaling of configs[1] over N GPUs (bench.py --gpus N): N cenX-like arrays, array j from seed 1 + j
-    **{f"cenx_dxz1_m1500_s{s}": dict(unit="supplementary_data/DXZ1_rc.fasta", multiplicity=1500, div_rate=0.01, seed=s)
-       for s in range(2, 9)},
+    # weak scaling of configs[1] over N GPUs (bench.py --gpus N): N cenX-like arrays.  Array j >= 2 has its OWN unit --
+    # DXZ1 with 30 % of its bases substituted (numpy default_rng(100 + j)) -- so that the arrays share no k-mers and the
+    # work per GPU stays that of configs[1] (arrays of one unit share their error k-mers: at 8 x 50x they enter the
+    # rare band and the pair increments per array nearly double); the array itself is made by the reference simulator
+    **{f"cenx_like_u{s}_m1500_s{s}": dict(unit="supplementary_data/DXZ1_rc.fasta", unit_subst=(0.30, 100 + s),
+                                         multiplicity=1500, div_rate=0.01, seed=s) for s in range(2, 9)},
     # configs[2]: the cen6-like array
     "cen6_d6z1_m1000_s4": dict(unit="supplementary_data/D6Z1.fasta", multiplicity=1000, div_rate=0.01, seed=4),
 }
@@ -52,7 +55,18 @@ def main():
         if os.path.exists(os.path.join(OUT, name + ".npz")) and "--force" not in sys.argv:
             continue
         with tempfile.TemporaryDirectory() as tmp:
-            argv = ["simulate_tandem_repeat.py", "--unit", os.path.join(REF, g["unit"]), "--multiplicity",
+            unit_path = os.path.join(REF, g["unit"])
+            if "unit_subst" in g:
+                from centroflye_b200.encode import codes_to_ascii
+                rate, useed = g["unit_subst"]
+                rng = np.random.default_rng(useed)
+                u = ascii_to_codes(read_fasta(unit_path).upper())
+                hit = rng.random(u.size) < rate
+                u[hit] = (u[hit] + rng.integers(1, 4, size=int(hit.sum()), dtype=np.uint8)) & 3
+                unit_path = os.path.join(tmp, "unit.fasta")
+                with open(unit_path, "w") as f:
+                    f.write(">unit\n" + codes_to_ascii(u) + "\n")
+            argv = ["simulate_tandem_repeat.py", "--unit", unit_path, "--multiplicity",
                     str(g["multiplicity"]), "--div-rate", str(g["div_rate"]), "--seed", str(g["seed"]), "-o", tmp]
             old_argv, old_path = sys.argv, list(sys.path)
             sys.argv = argv
@@ -65,7 +79,7 @@ def main():
             md5 = hashlib.md5(open(fasta, "rb").read()).hexdigest()
             flanked = read_fasta(fasta)
             tr = read_fasta(os.path.join(tmp, "tandem_repeat.fasta"))
-        unit = read_fasta(os.path.join(REF, g["unit"])).upper()
+            unit = read_fasta(unit_path).upper()
         start = (len(flanked) - len(tr)) // 2
         assert flanked[start:start + len(tr)] == tr and len(tr) == len(unit) * g["multiplicity"]
         codes = ascii_to_codes(flanked)
