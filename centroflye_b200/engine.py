@@ -452,6 +452,51 @@ class Engine:
             table = DocFreqTable(slots=dense[:2 * n], cap=n, dense=True)
         return rare, table
 
+    # -- the same two kernels without a host round trip per batch (streams of independent batches)
+    def docfreq_stream_launch(self, reads, k, band=None, with_counts=False, table_buf=None):
+        """Enqueue both phases of stage A for one batch and return a handle; nothing is read back yet, so the next
+        batch can be enqueued behind it.  docfreq_stream_finish(handle) waits for THIS batch's counters only."""
+        t = self.torch
+        total_k = max(reads.n_bases - reads.n_reads * (k - 1), 0)
+        n_parts, part_cap = self.stream_plan(total_k, reads.n_reads)
+        records, cursors, ecounters = self.emit_records(reads, k, n_parts, part_cap)
+        counters = self._counters()
+        rare, rare_nr, rare_nm, counters, max_rare = self.count_records(
+            records, cursors, n_parts, part_cap, k, band, with_counts, table_buf, counters=counters, group=self.stream_group)
+        stats = t.cat([counters, self.emit_stats(cursors, ecounters)])
+        host = t.empty(stats.numel(), dtype=t.int64, pin_memory=True)
+        host.copy_(stats, non_blocking=True)
+        done = t.cuda.Event()
+        done.record(t.cuda.current_stream(self.device))
+        return dict(reads=reads, k=k, band=band, with_counts=with_counts, table_buf=table_buf, n_parts=n_parts,
+                    rare=(rare, rare_nr, rare_nm), max_rare=max_rare, host=host, done=done, keep=(records, cursors))
+
+    def docfreq_stream_finish(self, h):
+        """-> (rare, table) of a launched batch, like docfreq_stream.  A batch whose buffers turned out too small (its
+        first of a kind, usually) is simply done again through the synchronous path."""
+        h["done"].synchronize()
+        c = h["host"]
+        if int(c[1]) or int(c[9]):
+            raise CfkError("stage A: shared-memory set overflowed (internal error)")
+        self.part_cap_seen[h["n_parts"]] = max(self.part_cap_seen.get(h["n_parts"], 0), int(c[10]))
+        n_rare = int(c[4])
+        if int(c[8]) or int(c[0]) or (h["band"] is not None and n_rare > h["max_rare"]):
+            if h["band"] is not None and n_rare > h["max_rare"]:
+                self.select_hint[("stream", bool(h["with_counts"]))] = n_rare + 1024
+            return self.docfreq_stream(h["reads"], h["k"], band=h["band"], with_counts=h["with_counts"],
+                                       want_table=h["table_buf"] is not None, table_buf=h["table_buf"])
+        self._adapt_stream_group(int(c[5]), h["n_parts"], int(c[6]))
+        table = None
+        if h["table_buf"] is not None:
+            n = int(c[5])
+            table = DocFreqTable(slots=h["table_buf"][:2 * n], cap=n, dense=True)
+        if h["band"] is None:
+            return None, table
+        rare, rare_nr, rare_nm = h["rare"]
+        if h["with_counts"]:
+            return (rare[:n_rare], rare_nr[:n_rare], rare_nm[:n_rare]), table
+        return rare[:n_rare], table
+
     def count_total(self, reads, batch, k, canonical=False):
         """Total occurrences of every k-mer over all reads (no per-read de-duplication) -> DocFreqTable whose n_reads
         field holds the count (better_consensus_unit_reconstruction.py:127-135).  canonical=True merges the two strands
@@ -544,7 +589,8 @@ class Engine:
     def build_index(self, keys, presorted=False):
         t = self.torch
         n = int(keys.numel())
-        sorted_keys = keys.contiguous() if presorted else self.sort_keys(keys.clone())
+        with self._stage("sort_rare"):
+            sorted_keys = keys.contiguous() if presorted else self.sort_keys(keys.clone())
         # slots per key: stage B probes this table once per k-mer and is bound by L2 sector throughput, so every probe
         # saved counts; 8x keeps chains near 1 probe while the table (12 B per slot) still sits in the 126 MB L2
         mult = self.index_cap_mult or (8 if n <= (1 << 20) else 4 if n <= (1 << 22) else 2)
@@ -552,8 +598,9 @@ class Engine:
         idx_keys = t.full((cap,), -1, dtype=t.int64, device=self.device)
         idx_vals = self._zeros(cap, t.int32)
         counters = self._counters()
-        _lib.call("cfk_index_build", self._p(sorted_keys), n, self._p(idx_keys), self._p(idx_vals), cap,
-                  self._p(counters), self._stream())
+        with self._stage("index_build"):
+            _lib.call("cfk_index_build", self._p(sorted_keys), n, self._p(idx_keys), self._p(idx_vals), cap,
+                      self._p(counters), self._stream())
         return KmerIndex(sorted_keys=sorted_keys, idx_keys=idx_keys, idx_vals=idx_vals, cap=cap, n=n)
 
     def index_from_host_keys(self, keys_u64):
@@ -647,8 +694,11 @@ class Engine:
                            selected=self._empty(0, t.int32)[:0], n_candidates=0, n_increments=0, n_splits=0)
         if n_kmers == 0 or csr.n_entries == 0 or max_d < max(min_d, 1):
             return empty
-        occ_ptr, occ, occ_last = (occurrences if occurrences is not None
-                                  else self.build_occurrences(csr, n_kmers, unit_lo, unit_hi, unit_last))
+        if occurrences is not None:
+            occ_ptr, occ, occ_last = occurrences
+        else:
+            with self._stage("occurrences"):
+                occ_ptr, occ, occ_last = self.build_occurrences(csr, n_kmers, unit_lo, unit_hi, unit_last)
         min_cov_u = int(min(max(min_cov, 0), U32_MAX))
         # stage C flavour: the sketch kernel serves min_cov in [3, 255]; the exact tables serve anything
         use_sketch = self.pair_mode != "exact" and SKETCH_MIN_COV <= min_cov_u <= SKETCH_MAX_COV
