@@ -115,6 +115,7 @@ class Engine:
         self.part_slack = 1.25  # records per partition buffer / expected records per partition (stream mode)
         self.stream_group = 1   # partitions per phase-2 unit; adapted after every call (_adapt_stream_group)
         self.part_cap_seen = {}  # n_parts -> largest partition (records) phase 1 produced so far
+        self._stat_pool, self._stat_next = [], 0  # pinned result slots of docfreq_stream_launch
         self.events = None  # set to a list to collect (stage, start_event, end_event) per C-ABI call group
         self._host_pool = {}  # name -> pinned uint8 buffer for results (to_host)
         self._copy_stream = None  # side stream of start_host_copy
@@ -235,28 +236,37 @@ class Engine:
     # ---- uploads ----------------------------------------------------------------------------
     def upload_reads(self, batch, k):
         """ReadBatch -> device (pinned staging, async copies)."""
-        order = np.argsort(-batch.read_len, kind="stable").astype(np.int32)
+        derived = batch.__dict__.setdefault("_cfk_derived", {})  # host arrays made once per (immutable) batch
+        if "order" not in derived:
+            derived["order"] = np.argsort(-batch.read_len, kind="stable").astype(np.int32)
+        order = derived["order"]
         packed = batch.packed.view(np.int32)
         h2d = packed.nbytes + batch.read_off.nbytes + batch.read_len.nbytes + order.nbytes
         return DeviceReads(packed=self._staged(batch, "packed", batch.packed),
                            read_off=self._staged(batch, "read_off", batch.read_off),
-                           read_len=self._staged(batch, "read_len", batch.read_len), order=self._to_dev(order),
+                           read_len=self._staged(batch, "read_len", batch.read_len),
+                           order=self._staged(batch, "order", order),
                            n_reads=batch.n_reads, n_bases=batch.n_bases, h2d_bytes=h2d,
                            max_len=int(batch.read_len.max()) if batch.n_reads else 0)
 
     def upload_units(self, units, k):
-        nk = np.maximum(units.unit_len.astype(np.int64) - k + 1, 0)
-        kbase = np.zeros(units.n_units + 1, dtype=np.int64)
-        np.cumsum(nk, out=kbase[1:])
-        last = np.zeros(units.n_units, dtype=np.int32)
-        ptr = units.read_unit_ptr
-        counts = np.diff(ptr)
-        last[:] = np.repeat(ptr[1:] - 1, counts)
+        derived = units.__dict__.setdefault("_cfk_derived", {})  # host arrays made once per (immutable) unit index
+        if ("kbase", k) not in derived:
+            nk = np.maximum(units.unit_len.astype(np.int64) - k + 1, 0)
+            kbase = np.zeros(units.n_units + 1, dtype=np.int64)
+            np.cumsum(nk, out=kbase[1:])
+            derived[("kbase", k)] = kbase
+        if "last" not in derived:
+            last = np.zeros(units.n_units, dtype=np.int32)
+            ptr = units.read_unit_ptr
+            last[:] = np.repeat(ptr[1:] - 1, np.diff(ptr))
+            derived["last"] = last
+        kbase, last = derived[("kbase", k)], derived["last"]
         h2d = units.unit_off.nbytes + units.unit_len.nbytes + kbase.nbytes + last.nbytes
         return DeviceUnits(unit_off=self._staged(units, "unit_off", units.unit_off),
                            unit_len=self._staged(units, "unit_len", units.unit_len),
-                           unit_kbase=self._to_dev(kbase), unit_last=self._to_dev(last), n_units=units.n_units,
-                           n_kmer_starts=int(kbase[-1]), h2d_bytes=h2d)
+                           unit_kbase=self._staged(units, f"kbase{k}", kbase), unit_last=self._staged(units, "last", last),
+                           n_units=units.n_units, n_kmer_starts=int(kbase[-1]), h2d_bytes=h2d)
 
     # ---- stage A ----------------------------------------------------------------------------
     def new_table(self, cap):
@@ -464,7 +474,10 @@ class Engine:
         rare, rare_nr, rare_nm, counters, max_rare = self.count_records(
             records, cursors, n_parts, part_cap, k, band, with_counts, table_buf, counters=counters, group=self.stream_group)
         stats = t.cat([counters, self.emit_stats(cursors, ecounters)])
-        host = t.empty(stats.numel(), dtype=t.int64, pin_memory=True)
+        if not self._stat_pool:  # page-locking costs far more than the copy: a small ring of pinned slots
+            self._stat_pool = [t.empty(16, dtype=t.int64, pin_memory=True) for _ in range(8)]
+        host = self._stat_pool[self._stat_next % len(self._stat_pool)][: stats.numel()]
+        self._stat_next += 1
         host.copy_(stats, non_blocking=True)
         done = t.cuda.Event()
         done.record(t.cuda.current_stream(self.device))
