@@ -51,8 +51,9 @@ constexpr int DE_WARPS = DE_THREADS / 32;
 #endif
 constexpr int DE_PER = CFK_DE_PER;          // consecutive k-mer starts per lane (2 or 4: the window holds 14 + 3 + 30 bases)
 constexpr int DE_CHUNK = 32 * DE_PER;       // k-mer starts per warp step
-constexpr int DE_DATA_WORDS = 57344;        // dynamic shared memory of the block (224 KB): [ read words | set ]
-constexpr int DE_MIN_SET = 16384;
+constexpr int DE_BLOCKS = 1024 / DE_THREADS;  // blocks sharing an SM (and its shared memory)
+constexpr int DE_DATA_WORDS = DE_BLOCKS == 1 ? 57344 : 57344 / DE_BLOCKS - 512;  // dynamic shared memory of a block: [ read words | set | queues ]
+constexpr int DE_MIN_SET = 16384 / DE_BLOCKS;
 constexpr uint32_t DE_MULTI = 0x80000000u;
 constexpr int DE_Q = 64;                          // queue entries per warp
 constexpr int DE_Q_WORDS = DE_WARPS * DE_Q * 2;   // the queues sit behind the set
@@ -317,7 +318,7 @@ __device__ __forceinline__ void de_scan_emit(const uint32_t* words, const uint32
   }
 }
 
-__global__ void __launch_bounds__(DE_THREADS, 1)
+__global__ void __launch_bounds__(DE_THREADS, DE_BLOCKS)
 docfreq_emit_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ read_off,
                     const int64_t* __restrict__ read_len, const int32_t* __restrict__ order,
                     const int64_t* __restrict__ item_ptr, int64_t n_reads, int k, uint64_t* __restrict__ records,
@@ -709,7 +710,7 @@ int cfk_docfreq_emit(const uint32_t* packed, const int64_t* read_off, const int6
     cudaError_t e = ensure_dynamic_smem(docfreq_emit_kernel, smem, &attr_done);
     if (e != cudaSuccess) return fail(CFK_ERR_CUDA, "cfk_docfreq_emit: cudaFuncSetAttribute", e);
   }
-  docfreq_emit_kernel<<<(unsigned)n_blocks, DE_THREADS, smem, (cudaStream_t)stream>>>(
+  docfreq_emit_kernel<<<(unsigned)n_blocks * DE_BLOCKS, DE_THREADS, smem, (cudaStream_t)stream>>>(
       packed, read_off, read_len, order, item_ptr, n_reads, k, records, part_cap, (uint32_t)n_parts, cursors, counters);
   CFK_CHECK_LAUNCH("docfreq_emit_kernel", 1);
   return CFK_OK;
