@@ -43,6 +43,10 @@ class CloudState:
         strs = ints_to_kmers(keys[ids[lo:hi]], self.k)
         return [set(strs[int(unit_ptr[u]) - lo:int(unit_ptr[u + 1]) - lo]) for u in range(u0, u1)]
 
+    def host_unit_sizes(self):
+        """int64[U]: cloud size of every unit (host copy of the CSR pointer, made once)."""
+        return np.diff(self.host()[0][: self.csr.n_units + 1]) if self.csr.n_units else np.zeros(0, dtype=np.int64)
+
     def with_csr(self, csr):
         return CloudState(self.engine, csr, self.index, self.unit_last, self.read_unit_ptr, self.r_ids, self.k)
 

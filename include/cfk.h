@@ -166,6 +166,38 @@ int cfk_kmer_count_canonical(const uint32_t* packed, const int64_t* read_off, co
                              const int64_t* tile_start, int64_t n_tiles, int k, uint64_t* table, int64_t cap,
                              int64_t* counters, cfk_stream_t stream);
 
+/* ---- read_placer scoring on the cloud CSR --------------------------------
+ * Replaces the data structures of ReadPlacer.add_reads, scripts/read_placer.py:42-94, and of CloudContig.add_read /
+ * update_mapping_scores, scripts/cloud_contig.py:26-41,87-95; the greedy loop (one read per iteration) stays on the
+ * host (centroflye_b200/read_placer.py).  All tables are caller-allocated, keys initialised to CFK_EMPTY_KEY, values 0.
+ *   cfk_placer_add_read       clouds[position + i][kmer] += 1 for the units u0 .. u0 + n_units - 1 of one read
+ *                             (cloud_contig.py:30-35) in the table contig_keys/contig_cnt keyed position << 32 | id;
+ *                             a (k-mer, position) whose counter reaches min_freq is appended to pairs[] as (id, position)
+ *                             (new_freq_kmers, :36-39) and marks freq_flag[id].  n_entries_max >= the read's cloud entries.
+ *   cfk_placer_initial_pairs  the list add_reads starts from (read_placer.py:54-57): every position of every k-mer
+ *                             with freq_flag set.
+ *   cfk_placer_update         update_mapping_scores (cloud_contig.py:87-95) for pairs[0 .. pair_counters[0]): every
+ *                             occurrence (unit g of read r = unit_read[g], position g - read_first_unit[r]) of the k-mer
+ *                             in a read with read_sel[r] and contig position >= position adds to the score of
+ *                             (r, contig position - position): m1 = set of (r, offset, position), m2[(r, offset)] =
+ *                             distinct positions << 32 | total -- (len(score), sum(score.values())) of :66-67.
+ *   cfk_placer_best           the selection of read_placer.py:61-79: one candidate per block (cfk_placer_best_blocks()
+ *                             blocks, 3 x uint64 each: score ; offset | rank << 32 ; read), 0 score = none.
+ * counters[0] = pairs appended, counters[1] != 0: a table or pairs[] is full (the caller grows and repeats). */
+int cfk_placer_best_blocks(void);
+int cfk_placer_add_read(const int64_t* unit_ptr, const uint32_t* ids, int64_t u0, int32_t n_units, int64_t n_entries_max,
+                        int64_t position, uint32_t min_freq, uint64_t* contig_keys, uint32_t* contig_cnt, int64_t cap,
+                        uint8_t* freq_flag, uint32_t* pairs, int64_t max_pairs, int64_t* counters, cfk_stream_t stream);
+int cfk_placer_initial_pairs(const uint64_t* contig_keys, int64_t cap, const uint8_t* freq_flag, uint32_t* pairs,
+                             int64_t max_pairs, int64_t* counters, cfk_stream_t stream);
+int cfk_placer_update(const uint32_t* pairs, const int64_t* pair_counters, int64_t max_pairs, const int64_t* occ_ptr,
+                      const uint32_t* occ, const int32_t* unit_read, const int64_t* read_first_unit, const uint8_t* read_sel,
+                      uint64_t* m1_keys, int64_t cap1, uint64_t* m2_keys, uint64_t* m2_val, int64_t cap2, int64_t* counters,
+                      cfk_stream_t stream);
+int cfk_placer_best(const uint64_t* m2_keys, const uint64_t* m2_val, int64_t cap2, const uint8_t* read_unused,
+                    const uint32_t* read_rank, uint32_t min_unit, uint32_t min_inters, uint32_t min_prop, uint64_t* out,
+                    cfk_stream_t stream);
+
 /* Merge (key, n_reads, n_multi) records counted elsewhere (another GPU's shard) into a table:
  * the owner-side half of the multi-GPU all-to-all.  counters[0] != 0: full. */
 int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n, uint64_t* table,
