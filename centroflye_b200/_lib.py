@@ -35,6 +35,8 @@ SIGNATURES = {
     "cfk_kmer_count_tile": (_int, []),
     "cfk_kmer_count_total": (_int, [_p, _p, _p, _p, _p, _i64, _int, _p, _i64, _p, _p]),
     "cfk_kmer_count_canonical": (_int, [_p, _p, _p, _p, _p, _i64, _int, _p, _i64, _p, _p]),
+    "cfk_kmer_position_keys": (_int, [_p, _i64, _int, _int, _p, _p]),
+    "cfk_adjacent_gaps": (_int, [_p, _i64, _int, _p, _p]),
     "cfk_placer_best_blocks": (_int, []),
     "cfk_placer_add_read": (_int, [_p, _p, _i64, _i32, _i64, _i64, _u32, _p, _p, _i64, _p, _p, _i64, _p, _p]),
     "cfk_placer_initial_pairs": (_int, [_p, _i64, _p, _p, _i64, _p, _p]),

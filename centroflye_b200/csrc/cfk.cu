@@ -517,6 +517,29 @@ kmer_count_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict
   }
 }
 
+// ---- per-read repetitive k-mers: scripts/unit_extractor.py:23-40 -----------------------
+// get_repetitive_kmers groups the positions of every k-mer of ONE sequence; get_convolution takes the gaps between
+// neighbouring positions of a k-mer.  Here: one sort key (k-mer << pos_bits | position) per k-mer start, sorted with
+// cfk_sort_u64; equal k-mers are then neighbours in position order and a gap is the difference of two neighbours.
+__global__ void kmer_position_keys_kernel(const uint32_t* __restrict__ words, int64_t n_kmers, int k, int pos_bits,
+                                          uint64_t* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_kmers) return;
+  keys[i] = (kmer_at(words, (uint32_t)i, k) << pos_bits) | (uint64_t)i;
+}
+
+// gaps[i] = position(i) - position(i - 1) when keys i - 1 and i hold the same k-mer, else 0 (also for i = 0)
+__global__ void adjacent_gaps_kernel(const uint64_t* __restrict__ keys, int64_t n, int pos_bits, uint32_t* __restrict__ gaps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t g = 0;
+  if (i > 0) {
+    const uint64_t a = keys[i - 1], b = keys[i];
+    if ((a >> pos_bits) == (b >> pos_bits)) g = (uint32_t)((b - a) & ((1ull << pos_bits) - 1ull));
+  }
+  gaps[i] = g;
+}
+
 __global__ void table_init_kernel(uint64_t* table, int64_t cap) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cap) reinterpret_cast<ulonglong2*>(table)[i] = make_ulonglong2(EMPTY, 0ull);
@@ -2437,6 +2460,25 @@ int cfk_kmer_count_canonical(const uint32_t* packed, const int64_t* read_off, co
 }
 
 int cfk_kmer_count_tile(void) { return KC_TILE; }
+
+int cfk_kmer_position_keys(const uint32_t* packed, int64_t n_bases, int k, int pos_bits, uint64_t* keys, cfk_stream_t stream) {
+  if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_kmer_position_keys: k must be in [1, 31]");
+  if (pos_bits < 1 || 2 * k + pos_bits > 63 || n_bases < 0 || n_bases >= (1ll << pos_bits) || n_bases >= (1ll << 32))
+    return fail(CFK_ERR_INVALID, "cfk_kmer_position_keys: need n_bases < 2^pos_bits and 2k + pos_bits <= 63");
+  const int64_t n = n_bases - k + 1;
+  if (n <= 0) return CFK_OK;
+  kmer_position_keys_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(packed, n, k, pos_bits, keys);
+  CFK_CHECK_LAUNCH("kmer_position_keys_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_adjacent_gaps(const uint64_t* keys, int64_t n, int pos_bits, uint32_t* gaps, cfk_stream_t stream) {
+  if (n < 0 || pos_bits < 1 || pos_bits > 62) return fail(CFK_ERR_INVALID, "cfk_adjacent_gaps: bad sizes");
+  if (n == 0) return CFK_OK;
+  adjacent_gaps_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, n, pos_bits, gaps);
+  CFK_CHECK_LAUNCH("adjacent_gaps_kernel", 1);
+  return CFK_OK;
+}
 
 int cfk_table_merge(const uint64_t* keys, const uint32_t* nreads, const uint32_t* nmulti, int64_t n, uint64_t* table,
                     int64_t cap, int64_t* counters, cfk_stream_t stream) {

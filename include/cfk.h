@@ -166,6 +166,15 @@ int cfk_kmer_count_canonical(const uint32_t* packed, const int64_t* read_off, co
                              const int64_t* tile_start, int64_t n_tiles, int k, uint64_t* table, int64_t cap,
                              int64_t* counters, cfk_stream_t stream);
 
+/* ---- repetitive k-mers of one sequence -----------------------------------
+ * Replaces get_repetitive_kmers + get_convolution, scripts/unit_extractor.py:23-40.  `packed` = the sequence 2-bit packed
+ * from base 0 (readable up to word n_bases / 16 + 2).  cfk_kmer_position_keys writes one key per k-mer start,
+ * k-mer << pos_bits | position; after cfk_sort_u64 the occurrences of a k-mer are neighbours in position order (the
+ * lists of :25-27) and cfk_adjacent_gaps gives gaps[i] = position(i) - position(i - 1) inside a k-mer's run, 0 at its
+ * first occurrence (the differences of :36). */
+int cfk_kmer_position_keys(const uint32_t* packed, int64_t n_bases, int k, int pos_bits, uint64_t* keys, cfk_stream_t stream);
+int cfk_adjacent_gaps(const uint64_t* keys, int64_t n, int pos_bits, uint32_t* gaps, cfk_stream_t stream);
+
 /* ---- read_placer scoring on the cloud CSR --------------------------------
  * Replaces the data structures of ReadPlacer.add_reads, scripts/read_placer.py:42-94, and of CloudContig.add_read /
  * update_mapping_scores, scripts/cloud_contig.py:26-41,87-95; the greedy loop (one read per iteration) stays on the
