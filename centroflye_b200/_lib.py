@@ -35,6 +35,7 @@ SIGNATURES = {
     "cfk_kmer_count_tile": (_int, []),
     "cfk_kmer_count_total": (_int, [_p, _p, _p, _p, _p, _i64, _int, _p, _i64, _p, _p]),
     "cfk_kmer_count_canonical": (_int, [_p, _p, _p, _p, _p, _i64, _int, _p, _i64, _p, _p]),
+    "cfk_merge_sorted_runs": (_int, [_p, _p, _i32, _i64, _p, _p]),
     "cfk_kmer_position_keys": (_int, [_p, _i64, _int, _int, _p, _p]),
     "cfk_adjacent_gaps": (_int, [_p, _i64, _int, _p, _p]),
     "cfk_placer_best_blocks": (_int, []),

@@ -774,6 +774,33 @@ __global__ void sort_disperse_kernel(uint64_t* d, int64_t n, int64_t hh, int64_t
   }
 }
 
+// Several sorted runs of DISTINCT keys, back to back (run j = keys[run_ptr[j] .. run_ptr[j + 1])), merged by ranking:
+// the place of a key in the merged order = its index in its own run + the number of smaller keys in every other run
+// (one binary search each).  Every rank of the multi-GPU path sorts its own rare keys; the all-gathered runs are
+// merged with this instead of one bitonic sort of the whole set (whose n log^2 n grows with the number of GPUs).
+__global__ void merge_runs_kernel(const uint64_t* __restrict__ keys, const int64_t* __restrict__ run_ptr, int n_runs,
+                                  uint64_t* __restrict__ out) {
+  const int64_t n = run_ptr[n_runs];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t x = keys[i];
+  int64_t rank = 0;
+  for (int j = 0; j < n_runs; ++j) {
+    int64_t lo = run_ptr[j], hi = run_ptr[j + 1];
+    if (i >= lo && i < hi) {
+      rank += i - lo;
+      continue;
+    }
+    const int64_t base = lo;
+    while (lo < hi) {  // first element of run j that is not smaller than x
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(keys + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    rank += lo - base;
+  }
+  out[rank] = x;
+}
+
 __global__ void index_build_kernel(const uint64_t* __restrict__ sorted_keys, int64_t n, uint64_t* idx_keys,
                                    uint32_t* idx_vals, int64_t cap, int64_t* counters) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2550,6 +2577,15 @@ int cfk_sort_u64(uint64_t* keys, int64_t n, cfk_stream_t stream) {
     ++launched;
   }
   CFK_CHECK_LAUNCH("sort_u64", launched);
+  return CFK_OK;
+}
+
+int cfk_merge_sorted_runs(const uint64_t* keys, const int64_t* run_ptr, int32_t n_runs, int64_t n, uint64_t* out,
+                          cfk_stream_t stream) {
+  if (n_runs < 1 || n < 0) return fail(CFK_ERR_INVALID, "cfk_merge_sorted_runs: bad sizes");
+  if (n == 0) return CFK_OK;
+  merge_runs_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(keys, run_ptr, n_runs, out);
+  CFK_CHECK_LAUNCH("merge_runs_kernel", 1);
   return CFK_OK;
 }
 

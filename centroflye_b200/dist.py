@@ -186,9 +186,17 @@ class ShardedRecruiter:
         mine, c = out
         eng._adapt_stream_group(int(c[5]), per, int(c[6]))
         with eng._stage("exchange_docfreq"):
-            allk, _ = all_gather_v(mine.contiguous(), self.group)
+            # every rank sorts its own keys; the gathered runs (distinct keys: a k-mer has one owner) are merged by rank
+            mine = eng.sort_keys(mine.contiguous().clone()) if mine.numel() > 1 else mine.contiguous()
+            allk, counts = all_gather_v(mine, self.group)
             self.bytes_exchanged += 8 * int(mine.numel())
-        return eng.sort_keys(allk.clone()) if allk.numel() else allk
+            if allk.numel() == 0:
+                return allk
+            run_ptr = eng._to_dev(np.concatenate([[0], np.cumsum(np.asarray(counts, dtype=np.int64))]))
+            merged = eng._empty(int(allk.numel()), t.int64)
+            _lib.call("cfk_merge_sorted_runs", eng._p(allk.contiguous()), eng._p(run_ptr), W, int(allk.numel()),
+                      eng._p(merged), eng._stream())
+        return merged[: int(allk.numel())]
 
     def global_rare_keys(self, table, lo, hi, max_nonuniq):
         """Local table -> sorted rare keys of the WHOLE read set (identical on every rank).

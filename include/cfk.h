@@ -245,6 +245,10 @@ int cfk_table_part_scatter(const uint64_t* table, int64_t cap, int32_t n_parts, 
  * of a k-mer in the sorted rare set is its integer id everywhere downstream (the reference's
  * kmer_index, distance_based_kmer_recruitment.py:103, canonicalised). */
 int cfk_sort_u64(uint64_t* keys, int64_t n, cfk_stream_t stream);
+/* n_runs sorted runs of pairwise DISTINCT keys, back to back (run j = keys[run_ptr[j] .. run_ptr[j + 1]), run_ptr[n_runs] =
+ * n on the device) -> out[0 .. n) sorted: the all-gathered, per-rank sorted rare keys of the multi-GPU path. */
+int cfk_merge_sorted_runs(const uint64_t* keys, const int64_t* run_ptr, int32_t n_runs, int64_t n, uint64_t* out,
+                          cfk_stream_t stream);
 
 /* Static probe table over the sorted rare keys: key -> rank.  idx_keys pre-filled with
  * CFK_EMPTY_KEY; cap >= 2 n recommended. */

@@ -398,3 +398,23 @@ def test_negative_max_nonuniq_selects_nothing(eng):
             assert eng.rare_kmers(eng.upload_reads(batch, 15), 15, 1, 100, 3).numel() > 0
         finally:
             eng.docfreq_mode = old
+
+
+def test_merge_sorted_runs(eng):
+    """cfk_merge_sorted_runs: runs of distinct keys (sizes 0, 1, many) merged by ranking == numpy sort."""
+    from centroflye_b200 import _lib
+    import torch
+    rng = np.random.default_rng(4)
+    keys = np.unique(rng.integers(0, 1 << 62, size=200000, dtype=np.int64))
+    rng.shuffle(keys)
+    sizes = [0, 1, 70000, 3, keys.size - 70004]
+    runs, at = [], 0
+    for s in sizes:
+        runs.append(np.sort(keys[at:at + s]))
+        at += s
+    cat = np.concatenate(runs)
+    ptr = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    d_cat, d_ptr = eng._to_dev(cat), eng._to_dev(ptr)
+    out = eng._empty(cat.size, torch.int64)
+    _lib.call("cfk_merge_sorted_runs", eng._p(d_cat), eng._p(d_ptr), len(sizes), int(cat.size), eng._p(out), eng._stream())
+    assert np.array_equal(out.cpu().numpy(), np.sort(keys))
