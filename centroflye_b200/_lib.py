@@ -50,7 +50,8 @@ SIGNATURES = {
     "cfk_table_part_scatter": (_int, [_p, _i64, _i32, _p, _p, _p, _p, _p]),
     "cfk_sort_u64": (_int, [_p, _i64, _p]),
     "cfk_index_build": (_int, [_p, _i64, _p, _p, _i64, _p, _p]),
-    "cfk_cloud_build": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _i64, _p, _p, _p]),
+    "cfk_cloud_build": (_int, [_p, _p, _p, _p, _i64, _int, _p, _p, _i64, _p, _i32, _p, _p, _p]),
+    "cfk_index_filter_build": (_int, [_p, _i64, _i32, _p, _p]),
     "cfk_scan_scratch_elems": (_i64, [_i64]),
     "cfk_exclusive_scan": (_int, [_p, _p, _i64, _p, _p]),
     "cfk_cloud_compact": (_int, [_p, _p, _p, _i64, _p, _p]),

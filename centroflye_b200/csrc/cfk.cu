@@ -801,6 +801,13 @@ __global__ void merge_runs_kernel(const uint64_t* __restrict__ keys, const int64
   out[rank] = x;
 }
 
+__global__ void index_filter_kernel(const uint64_t* __restrict__ sorted_keys, int64_t n, int filter_bits, uint32_t* filter) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t b = mix64(sorted_keys[i]) >> (64 - filter_bits);
+  atomicOr(filter + (b >> 5), 1u << (b & 31u));
+}
+
 __global__ void index_build_kernel(const uint64_t* __restrict__ sorted_keys, int64_t n, uint64_t* idx_keys,
                                    uint32_t* idx_vals, int64_t cap, int64_t* counters) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -980,7 +987,7 @@ __global__ void __launch_bounds__(CLW_WARPS * 32)
 cloud_build_warp_kernel(const uint32_t* __restrict__ packed, const int64_t* __restrict__ unit_off,
                         const int32_t* __restrict__ unit_len, const int64_t* __restrict__ unit_kbase, int64_t n_units, int k,
                         const uint64_t* __restrict__ idx_keys, const uint32_t* __restrict__ idx_vals, int64_t cap,
-                        uint32_t* tmp_ids, int32_t* unit_cnt) {
+                        const uint32_t* __restrict__ filter, int filter_bits, uint32_t* tmp_ids, int32_t* unit_cnt) {
   __shared__ uint32_t s_list[CLW_WARPS][CLW_LIST];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -1024,9 +1031,19 @@ cloud_build_warp_kernel(const uint32_t* __restrict__ packed, const int64_t* __re
           if ((pos & 15) == 0) word = __ldg(packed + (pos >> 4));
           kmer = ((kmer << 2) | ((word >> ((pos & 15) << 1)) & 3u)) & mask;
           ++pos;
-          km[j] = kmer;
-          slot[j] = home_slot(mix64(kmer), cap);
-          key[j] = __ldg(idx_keys + slot[j]);
+          const uint64_t h = mix64(kmer);
+          // index larger than L2 (the rare set of several GPUs): one bit per hash prefix, L2 resident, answers "not
+          // rare" for the ~97 % of k-mers that are not, before the probe that would go to DRAM
+          bool maybe = true;
+          if (filter != nullptr) {
+            const uint64_t b = h >> (64 - filter_bits);
+            maybe = (__ldg(filter + (b >> 5)) >> (b & 31u)) & 1u;
+          }
+          if (maybe) {
+            km[j] = kmer;
+            slot[j] = home_slot(h, cap);
+            key[j] = __ldg(idx_keys + slot[j]);
+          }
         }
       }
 #pragma unroll
@@ -2589,6 +2606,14 @@ int cfk_merge_sorted_runs(const uint64_t* keys, const int64_t* run_ptr, int32_t 
   return CFK_OK;
 }
 
+int cfk_index_filter_build(const uint64_t* sorted_keys, int64_t n, int32_t filter_bits, uint32_t* filter, cfk_stream_t stream) {
+  if (n < 0 || filter_bits < 5 || filter_bits > 36) return fail(CFK_ERR_INVALID, "cfk_index_filter_build: bad sizes");
+  if (n == 0) return CFK_OK;
+  index_filter_kernel<<<(unsigned)blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(sorted_keys, n, filter_bits, filter);
+  CFK_CHECK_LAUNCH("index_filter_kernel", 1);
+  return CFK_OK;
+}
+
 int cfk_index_build(const uint64_t* sorted_keys, int64_t n, uint64_t* idx_keys, uint32_t* idx_vals, int64_t cap,
                     int64_t* counters, cfk_stream_t stream) {
   if (n < 0 || cap < 1 || n >= (1ll << 32) - 1) return fail(CFK_ERR_INVALID, "cfk_index_build: bad sizes");
@@ -2601,9 +2626,11 @@ int cfk_index_build(const uint64_t* sorted_keys, int64_t n, uint64_t* idx_keys, 
 
 int cfk_cloud_build(const uint32_t* packed, const int64_t* unit_off, const int32_t* unit_len,
                     const int64_t* unit_kbase, int64_t n_units, int k, const uint64_t* idx_keys,
-                    const uint32_t* idx_vals, int64_t cap, uint32_t* tmp_ids, int32_t* unit_cnt, cfk_stream_t stream) {
+                    const uint32_t* idx_vals, int64_t cap, const uint32_t* filter, int32_t filter_bits, uint32_t* tmp_ids,
+                    int32_t* unit_cnt, cfk_stream_t stream) {
   if (k < 1 || k > 31) return fail(CFK_ERR_INVALID, "cfk_cloud_build: k must be in [1, 31]");
   if (n_units < 0 || n_units >= (1ll << 31) || cap < 1) return fail(CFK_ERR_INVALID, "cfk_cloud_build: bad sizes");
+  if (filter != nullptr && (filter_bits < 5 || filter_bits > 36)) return fail(CFK_ERR_INVALID, "cfk_cloud_build: filter_bits");
   if (n_units == 0) return CFK_OK;
   static const bool block_form = [] { const char* e = getenv("CFK_CLOUD_MODE"); return e && !strcmp(e, "block"); }();
   if (block_form) {  // the first version of the kernel, one block per unit (A/B and cross-checks)
@@ -2613,7 +2640,7 @@ int cfk_cloud_build(const uint32_t* packed, const int64_t* unit_off, const int32
     return CFK_OK;
   }
   cloud_build_warp_kernel<<<(unsigned)blocks_for(n_units, CLW_WARPS), CLW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      packed, unit_off, unit_len, unit_kbase, n_units, k, idx_keys, idx_vals, cap, tmp_ids, unit_cnt);
+      packed, unit_off, unit_len, unit_kbase, n_units, k, idx_keys, idx_vals, cap, filter, filter_bits, tmp_ids, unit_cnt);
   CFK_CHECK_LAUNCH("cloud_build_warp_kernel", 1);
   return CFK_OK;
 }

@@ -69,6 +69,8 @@ class KmerIndex:
     idx_vals: object     # int32[cap]
     cap: int
     n: int
+    filter: object = None   # int32[2^filter_bits / 32] bitmap of hash prefixes, only for an index beyond L2
+    filter_bits: int = 0
 
 
 @dataclass
@@ -104,6 +106,7 @@ class Engine:
         self.sketch_banked = 1    # stage C sketch: bank-aware placement of the codes (0: the ids' own order)
         self.use_occ_last = 1     # stage C/D read unit_last through a per-occurrence copy (0: chase unit_last[g])
         self.index_cap_mult = 0   # slots per key of the rare-set probe table; 0 = by size (build_index)
+        self.index_filter_bytes = 96 << 20  # a probe table larger than this gets a bitmap pre-filter (cfk_index_filter_build)
         self.table_load = 0.75  # distinct k-mers <= occurrences, so the stage-A table is at most this full (measured: 0.45 / 0.6 / 0.75 -> 26.4 / 26.0 / 25.8 ms per step)
         # stage C kernel: "auto" = sketch where it applies, "exact" = always the exact tables, "sketch" = insist
         self.pair_mode = os.environ.get("CFK_PAIR_MODE", "auto")
@@ -614,7 +617,13 @@ class Engine:
         with self._stage("index_build"):
             _lib.call("cfk_index_build", self._p(sorted_keys), n, self._p(idx_keys), self._p(idx_vals), cap,
                       self._p(counters), self._stream())
-        return KmerIndex(sorted_keys=sorted_keys, idx_keys=idx_keys, idx_vals=idx_vals, cap=cap, n=n)
+        filt, bits = None, 0
+        if 12 * cap > self.index_filter_bytes:  # stage B would probe DRAM: a bitmap that stays in L2 goes first
+            bits = int(min(30, max(20, math.ceil(math.log2(max(16 * n, 2))))))  # >= 16 bits per key: ~6 % false positives
+            filt = self._zeros((1 << bits) // 32, t.int32)
+            _lib.call("cfk_index_filter_build", self._p(sorted_keys), n, bits, self._p(filt), self._stream())
+        return KmerIndex(sorted_keys=sorted_keys, idx_keys=idx_keys, idx_vals=idx_vals, cap=cap, n=n, filter=filt,
+                         filter_bits=bits)
 
     def index_from_host_keys(self, keys_u64):
         """Sorted unique uint64 numpy keys -> KmerIndex (genomic_kmers arriving as set[str])."""
@@ -641,7 +650,7 @@ class Engine:
         with self._stage("cloud_build"):
             _lib.call("cfk_cloud_build", self._p(reads.packed), self._p(units.unit_off), self._p(units.unit_len),
                       self._p(units.unit_kbase), U, k, self._p(index.idx_keys), self._p(index.idx_vals), index.cap,
-                      self._p(tmp), self._p(cnt), self._stream())
+                      self._p(index.filter), int(index.filter_bits), self._p(tmp), self._p(cnt), self._stream())
         unit_ptr = self.exclusive_scan(cnt[:U])
         E = int(unit_ptr[U].item())
         ids = self._empty(E, t.int32)

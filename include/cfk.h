@@ -264,7 +264,13 @@ int cfk_index_build(const uint64_t* sorted_keys, int64_t n, uint64_t* idx_keys, 
 int cfk_cloud_build(const uint32_t* packed, const int64_t* unit_off, const int32_t* unit_len,
                     const int64_t* unit_kbase, int64_t n_units, int k,
                     const uint64_t* idx_keys, const uint32_t* idx_vals, int64_t cap,
+                    const uint32_t* filter, int32_t filter_bits,
                     uint32_t* tmp_ids, int32_t* unit_cnt, cfk_stream_t stream);
+/* Optional pre-filter of cfk_cloud_build for an index that does not fit L2 (the rare set of several GPUs): a bitmap of
+ * 2^filter_bits bits (zeroed by the caller), bit mix64(key) >> (64 - filter_bits) set for every key.  A clear bit
+ * proves "not in the set"; a set bit sends the k-mer to the index as before, so results do not depend on it.
+ * filter = NULL: every k-mer probes the index. */
+int cfk_index_filter_build(const uint64_t* sorted_keys, int64_t n, int32_t filter_bits, uint32_t* filter, cfk_stream_t stream);
 /* out[0] = 0, out[i + 1] = in[0] + ... + in[i]  (int32 -> int64); scratch holds
  * cfk_scan_scratch_elems(n) int64. */
 int64_t cfk_scan_scratch_elems(int64_t n);

@@ -418,3 +418,28 @@ def test_merge_sorted_runs(eng):
     out = eng._empty(cat.size, torch.int64)
     _lib.call("cfk_merge_sorted_runs", eng._p(d_cat), eng._p(d_ptr), len(sizes), int(cat.size), eng._p(out), eng._stream())
     assert np.array_equal(out.cpu().numpy(), np.sort(keys))
+
+
+def test_cloud_build_with_index_filter(eng):
+    """The bitmap pre-filter of stage B (cfk_index_filter_build; used when the rare-set index outgrows L2) must not change
+    a single cloud: same CSR with the filter forced on as without it."""
+    import bench
+    unit, batch, units = bench.simulate("cenx", 0.03)
+    k = 19
+    reads, dunits = eng.upload_reads(batch, k), eng.upload_units(units, k)
+    rare = eng.rare_kmers(reads, k, 6, 40, 3)
+    assert rare.numel() > 1000
+    old = eng.index_filter_bytes
+    try:
+        eng.index_filter_bytes = 1 << 60
+        plain = eng.build_index(rare)
+        assert plain.filter is None
+        eng.index_filter_bytes = 0
+        filtered = eng.build_index(rare)
+        assert filtered.filter is not None and filtered.filter_bits >= 20
+    finally:
+        eng.index_filter_bytes = old
+    a, b = eng.build_clouds(reads, dunits, k, plain), eng.build_clouds(reads, dunits, k, filtered)
+    assert a.n_entries == b.n_entries > 0
+    assert np.array_equal(a.unit_ptr.cpu().numpy(), b.unit_ptr.cpu().numpy())
+    assert np.array_equal(a.ids.cpu().numpy(), b.ids.cpu().numpy())
