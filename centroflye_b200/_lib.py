@@ -38,6 +38,9 @@ SIGNATURES = {
     "cfk_merge_sorted_runs": (_int, [_p, _p, _i32, _i64, _p, _p]),
     "cfk_kmer_position_keys": (_int, [_p, _i64, _int, _int, _p, _p]),
     "cfk_adjacent_gaps": (_int, [_p, _i64, _int, _p, _p]),
+    "cfk_rr_max_symbols": (_int, []),
+    "cfk_rr_words": (_int, [_i32]),
+    "cfk_rr_filter": (_int, [_p, _p, _p, _p, _i64, _p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "cfk_placer_best_blocks": (_int, []),
     "cfk_placer_add_read": (_int, [_p, _p, _i64, _i32, _i64, _i64, _u32, _p, _p, _i64, _p, _p, _i64, _p, _p]),
     "cfk_placer_initial_pairs": (_int, [_p, _i64, _p, _p, _i64, _p, _p]),

@@ -10,8 +10,9 @@ INGEST_SRC = os.path.join(HERE, "csrc", "ncrf_ingest.cpp")  # host-side NCRF ing
 WRITER_SRC = os.path.join(HERE, "csrc", "result_writer.cpp")  # host-side edge file writer, same library
 STREAM_SRC = os.path.join(HERE, "csrc", "docfreq_stream.cu")  # stage A, two-phase form (emit + apply)
 PLACER_SRC = os.path.join(HERE, "csrc", "placer.cu")  # read_placer scoring on the cloud CSR (row f rank 2)
+RR_SRC = os.path.join(HERE, "csrc", "rr_filter.cu")  # read recruitment pre-filter (row f rank 4)
 COMMON_HDR = os.path.join(HERE, "csrc", "cfk_common.cuh")
-SOURCES = [SRC, STREAM_SRC, PLACER_SRC, INGEST_SRC, WRITER_SRC]
+SOURCES = [SRC, STREAM_SRC, PLACER_SRC, RR_SRC, INGEST_SRC, WRITER_SRC]
 HDR = os.path.join(os.path.dirname(HERE), "include", "cfk.h")
 OUT = os.path.join(HERE, "libcfk.so")
 

@@ -155,12 +155,13 @@ class ShardedRecruiter:
         per = n_parts // W
         for attempt in range(3):
             records, cursors, ecounters = eng.emit_records(self.reads, self.k, n_parts, part_cap)
-            with eng._stage("exchange_docfreq"):
+            with eng._stage("exchange_pack"):
                 counts = cursors.clamp(max=part_cap)
                 offsets = eng.exclusive_scan(counts)
                 send = eng._empty(self.n_kmers_local, t.int64)  # records <= k-mer occurrences
                 _lib.call("cfk_records_pack", eng._p(records), part_cap, eng._p(counts), eng._p(offsets), n_parts,
                           eng._p(send), eng._stream())
+            with eng._stage("exchange_docfreq"):
                 recv, recv_counts, flags, n_sent = exchange_records(send, counts, W, self.group,
                                                                     flags=eng.emit_stats(cursors, ecounters))
             self.bytes_exchanged += 8 * n_sent + 4 * n_parts
@@ -185,7 +186,7 @@ class ShardedRecruiter:
             return None
         mine, c = out
         eng._adapt_stream_group(int(c[5]), per, int(c[6]))
-        with eng._stage("exchange_docfreq"):
+        with eng._stage("exchange_rare"):
             # every rank sorts its own keys; the gathered runs (distinct keys: a k-mer has one owner) are merged by rank
             mine = eng.sort_keys(mine.contiguous().clone()) if mine.numel() > 1 else mine.contiguous()
             allk, counts = all_gather_v(mine, self.group)

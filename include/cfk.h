@@ -175,6 +175,24 @@ int cfk_kmer_count_canonical(const uint32_t* packed, const int64_t* read_off, co
 int cfk_kmer_position_keys(const uint32_t* packed, int64_t n_bases, int k, int pos_bits, uint64_t* keys, cfk_stream_t stream);
 int cfk_adjacent_gaps(const uint64_t* keys, int64_t n, int pos_bits, uint32_t* gaps, cfk_stream_t stream);
 
+/* ---- read recruitment pre-filter (second half) ---------------------------------
+ * Replaces the two edlibAlign(unit / reverse complement, read, k = threshold, EDLIB_MODE_HW, EDLIB_TASK_DISTANCE) calls
+ * of scripts/read_recruitment/rr.cpp:73-90: out_keep[r] = 1 when the best edit distance of the whole unit against any
+ * infix of read r, on either strand, is <= threshold (threshold < 0: no limit, as edlib's k = -1).  Bit-parallel
+ * (Myers / Hyyro) on 64-bit words, one thread per (read, strand).
+ *   text      all reads as bytes, every read on a 16-byte boundary, 16 readable bytes behind the last one
+ *   peq       [2 strands][cfk_rr_max_symbols()][cfk_rr_words(m)] match masks: bit i of word w of symbol s = the unit
+ *             (strand 0) / its reverse complement (strand 1) has symbol s at base 64 w + i; symbol slot 0 = all zero
+ *   sym_of    [256] byte -> symbol slot (0 for bytes the unit does not contain: they match nothing, as in edlib)
+ *   out_dist  NULL, or [2 * n_reads]: the best distance seen per (read, strand) -- the exact infix distance when
+ *             exact != 0, otherwise the first value <= threshold (the scan of a strand stops there)
+ * out_keep is zeroed by the caller.  Units of up to 3328 bases. */
+int cfk_rr_max_symbols(void);
+int cfk_rr_words(int32_t m);
+int cfk_rr_filter(const uint8_t* text, const int64_t* read_off, const int64_t* read_len, const int32_t* order, int64_t n_reads,
+                  const uint64_t* peq, const uint8_t* sym_of, int32_t m, int32_t threshold, int32_t exact, int32_t* out_dist,
+                  uint8_t* out_keep, cfk_stream_t stream);
+
 /* ---- read_placer scoring on the cloud CSR --------------------------------
  * Replaces the data structures of ReadPlacer.add_reads, scripts/read_placer.py:42-94, and of CloudContig.add_read /
  * update_mapping_scores, scripts/cloud_contig.py:26-41,87-95; the greedy loop (one read per iteration) stays on the
