@@ -105,9 +105,9 @@ def recruit(unit, seqs, threshold, exact=False, engine=None):
         n = end - start
         d_keep = eng._zeros(n, t.uint8)
         d_dist = eng._empty(2 * n, t.int32) if exact else None
-        _lib.call("cfk_rr_filter", eng._p(eng._to_dev(text)), eng._p(eng._to_dev(offs)), eng._p(eng._to_dev(lens)),
-                  eng._p(eng._to_dev(order)), n, eng._p(d_peq), eng._p(d_sym), len(unit), int(threshold), int(bool(exact)),
-                  eng._p(d_dist), eng._p(d_keep), eng._stream())
+        d_text, d_offs, d_lens, d_order = eng._to_dev(text), eng._to_dev(offs), eng._to_dev(lens), eng._to_dev(order)
+        _lib.call("cfk_rr_filter", eng._p(d_text), eng._p(d_offs), eng._p(d_lens), eng._p(d_order), n, eng._p(d_peq),
+                  eng._p(d_sym), len(unit), int(threshold), int(bool(exact)), eng._p(d_dist), eng._p(d_keep), eng._stream())
         keep[start:end] = d_keep[:n].cpu().numpy().astype(bool)
         if exact:
             dist[start:end] = d_dist[: 2 * n].cpu().numpy().reshape(n, 2)
