@@ -62,7 +62,7 @@ def build_masks(unit):
     if nw < 0:
         raise CfkError(f"read recruitment: the unit has {m} bases; 1..3328 are supported")
     n_sym = int(lib.cfk_rr_max_symbols())
-    symbols = sorted(set(unit.encode("latin-1")))
+    symbols = sorted(set((unit + reverse_complement(unit)).encode("latin-1")))  # both strands share one symbol table
     if len(symbols) > n_sym - 1:
         raise CfkError(f"read recruitment: the unit uses {len(symbols)} distinct symbols; at most {n_sym - 1} are supported")
     sym_of = np.zeros(256, dtype=np.uint8)
