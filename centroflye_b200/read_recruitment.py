@@ -15,6 +15,7 @@ from . import _lib
 from ._lib import CfkError
 
 _COMPLEMENT = {"A": "T", "T": "A", "G": "C", "C": "G"}
+SEGMENT = 8192  # read bases per device work item (a multiple of 16: segments start on 16-byte boundaries)
 
 
 def reverse_complement(unit):
@@ -101,14 +102,30 @@ def recruit(unit, seqs, threshold, exact=False, engine=None):
         text = np.zeros(int(offs[-1] + ((lens[-1] + 15) & ~15)) + 16, dtype=np.uint8)
         for o, s in zip(offs.tolist(), seqs[start:end]):
             text[o:o + len(s)] = np.frombuffer(s.encode("latin-1"), dtype=np.uint8)
-        order = np.argsort(-lens, kind="stable").astype(np.int32)
-        n = end - start
+        # One thread walks one segment.  A hit within `threshold` edits spans at most |unit| + threshold read bases, so a
+        # long read is cut into segments of SEGMENT bases that overlap by that much: the decision per read (any segment
+        # hits) is unchanged, the longest read no longer sets the kernel's duration.  Exact distances need whole reads.
+        seg_read = np.arange(end - start, dtype=np.int64)
+        seg_off, seg_len = offs, lens
+        if not exact and threshold >= 0:
+            overlap = len(unit) + int(threshold)
+            n_seg = np.maximum(1, -(-np.maximum(lens - overlap, 1) // SEGMENT))
+            seg_read = np.repeat(seg_read, n_seg)
+            first = np.cumsum(n_seg) - n_seg
+            j = np.arange(int(n_seg.sum()), dtype=np.int64) - np.repeat(first, n_seg)
+            seg_off = offs[seg_read] + j * SEGMENT
+            seg_len = np.minimum(SEGMENT + overlap, lens[seg_read] - j * SEGMENT)
+        order = np.argsort(-seg_len, kind="stable").astype(np.int32)
+        n = int(seg_read.size)
         d_keep = eng._zeros(n, t.uint8)
         d_dist = eng._empty(2 * n, t.int32) if exact else None
-        d_text, d_offs, d_lens, d_order = eng._to_dev(text), eng._to_dev(offs), eng._to_dev(lens), eng._to_dev(order)
-        _lib.call("cfk_rr_filter", eng._p(d_text), eng._p(d_offs), eng._p(d_lens), eng._p(d_order), n, eng._p(d_peq),
-                  eng._p(d_sym), len(unit), int(threshold), int(bool(exact)), eng._p(d_dist), eng._p(d_keep), eng._stream())
-        keep[start:end] = d_keep[:n].cpu().numpy().astype(bool)
+        d_text, d_offs, d_lens, d_order = eng._to_dev(text), eng._to_dev(seg_off), eng._to_dev(seg_len), eng._to_dev(order)
+        with eng._stage("rr_filter"):
+            _lib.call("cfk_rr_filter", eng._p(d_text), eng._p(d_offs), eng._p(d_lens), eng._p(d_order), n, eng._p(d_peq),
+                      eng._p(d_sym), len(unit), int(threshold), int(bool(exact)), eng._p(d_dist), eng._p(d_keep), eng._stream())
+        hit = np.zeros(end - start, dtype=bool)
+        np.logical_or.at(hit, seg_read, d_keep[:n].cpu().numpy().astype(bool))
+        keep[start:end] = hit
         if exact:
             dist[start:end] = d_dist[: 2 * n].cpu().numpy().reshape(n, 2)
         start = end
