@@ -25,7 +25,7 @@ import numpy as np
 
 from .encode import check_k, ints_to_kmers, kmers_to_ints
 from .engine import band_to_int, default_engine, to_host_u32, to_host_u64, U32_MAX
-from .ncrf_parser import NCRF_Report
+from .ncrf_parser import LazyNCRF_Report, NCRF_Report
 from .read_kmer_cloud import (CloudDict, get_reads_kmer_clouds, report_device_reads, state_from_sets)
 from .utils.os_utils import smart_makedirs
 
@@ -351,7 +351,7 @@ def main(argv=None):
     params = parse_args(argv)
     smart_makedirs(params.outdir)
 
-    reads_ncrf_report = NCRF_Report(params.ncrf)
+    reads_ncrf_report = LazyNCRF_Report(params.ncrf)  # Python records only if somebody asks for them
     stamp.append(("parse_report", time.perf_counter()))
     rare_kmers = get_rare_kmers(reads_ncrf_report,
                                 k=params.k,

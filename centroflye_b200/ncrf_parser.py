@@ -167,3 +167,24 @@ class NCRF_Report:
     def get_motif_alignments(self, n=1):
         """r_id -> unit alignments of its record (scripts/ncrf_parser.py:170-174)."""
         return {r_id: record.get_motif_alignments(n=n) for r_id, record in self.records.items()}
+
+
+class LazyNCRF_Report(NCRF_Report):
+    """An NCRF_Report that parses its file into Python records only when somebody looks at them.
+
+    The command line of distance_based_kmer_recruitment.py hands the report straight to the device path, which ingests
+    the FILE natively (csrc/ncrf_ingest.cpp) and never touches ``records``: building 10^4 record objects with 80 kB
+    strings each (0.5 s for a 320 MB report) would be the slowest step of the run.  Any access to an attribute of the
+    eager class (``records``, ``read_lens``, ``classify`` ...) runs the eager constructor first, so callers see the same
+    object either way; while it is unparsed nobody can have edited a record, so the device path may trust the file."""
+
+    def __init__(self, report_fn, min_record_len=5000):
+        self.__dict__["_cfk_source"] = (report_fn, min_record_len)
+        self.__dict__["_cfk_lazy_unparsed"] = True
+
+    def __getattr__(self, name):  # only called for attributes that are not there (yet)
+        if name.startswith("_cfk") or not self.__dict__.get("_cfk_lazy_unparsed", False):
+            raise AttributeError(name)
+        self.__dict__["_cfk_lazy_unparsed"] = False
+        NCRF_Report.__init__(self, *self.__dict__["_cfk_source"])
+        return getattr(self, name)

@@ -112,10 +112,16 @@ class CloudDict(dict):
 
 
 # ---- per-report caches (parse once, upload once) ---------------------------------------------
+def _unparsed(report):
+    """A LazyNCRF_Report nobody has looked into yet: its file is the only copy of the records."""
+    return bool(getattr(report, "_cfk_lazy_unparsed", False))
+
+
 def _report_cache(report):
     cache = getattr(report, "_cfk_cache", None)
-    if cache is None or cache.get("n_records") != len(report.records):
-        cache = {"n_records": len(report.records), "units": {}, "dev_reads": {}, "dev_units": {}}
+    n_records = -1 if _unparsed(report) else len(report.records)
+    if cache is None or (n_records >= 0 and cache.get("n_records") not in (-1, n_records)):
+        cache = {"n_records": n_records, "units": {}, "dev_reads": {}, "dev_units": {}}
         try:
             report._cfk_cache = cache
         except AttributeError:
@@ -134,6 +140,8 @@ def _native(report, n):
         batch, units, _ = native_ingest(src[0], n=n, min_record_len=src[1])
     except (OSError, ValueError):
         return None  # the Python path below raises the reference-shaped error, if any
+    if _unparsed(report):
+        return batch, units  # no Python record exists that could disagree with the file
     if batch.r_ids != list(report.records.keys()):
         return None
     # a caller may have edited records in place since the file was parsed: the file is only trusted while every

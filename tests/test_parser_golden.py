@@ -83,3 +83,23 @@ def test_units_from_report_takes_reference_style_records(golden):
         got = units_from_report(duck, batch_from_report(duck), n=n)
         assert np.array_equal(got.read_unit_ptr, want.read_unit_ptr)
         assert np.array_equal(got.unit_off, want.unit_off) and np.array_equal(got.unit_len, want.unit_len)
+
+
+def test_lazy_report_is_the_eager_report_once_looked_at(golden):
+    """LazyNCRF_Report (what the command line builds) parses on first attribute access and is then indistinguishable
+    from NCRF_Report; private _cfk attributes never trigger the parse."""
+    from centroflye_b200.ncrf_parser import LazyNCRF_Report
+    g = golden(golden_cases()[0])
+    lazy, eager = LazyNCRF_Report(g.report_path), NCRF_Report(g.report_path)
+    assert lazy._cfk_lazy_unparsed and getattr(lazy, "_cfk_cache", None) is None and lazy._cfk_lazy_unparsed
+    assert isinstance(lazy, NCRF_Report)
+    assert list(lazy.records.keys()) == list(eager.records.keys())        # first look: parsed now
+    assert not lazy._cfk_lazy_unparsed
+    for r_id, rec in eager.records.items():
+        assert vars(lazy.records[r_id]) == vars(rec)
+    assert lazy.read_lens == eager.read_lens and lazy.discarded_reads == eager.discarded_reads
+    assert lazy.classify(large_threshold=3000) == eager.classify(large_threshold=3000)
+    with pytest.raises(AttributeError):
+        lazy.no_such_attribute
+    with pytest.raises(FileNotFoundError):
+        LazyNCRF_Report("/no/such/report.ncrf").records
