@@ -105,22 +105,27 @@ def band(params=None):
 
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  A step lasts tens
-    of milliseconds, so the sampler reads NVML directly (nvidia_ml_py, ~5 ms period) and falls back to polling
-    nvidia-smi only if NVML cannot be loaded."""
+    of milliseconds, so the sampler reads NVML directly (nvidia_ml_py) and falls back to polling nvidia-smi only if
+    NVML cannot be loaded.  One GPU: every 5 ms (no measurable effect on the step).  Several ranks: ONLY rank 0
+    samples, every GPU of the job, every 25 ms -- eight processes polling NVML every 5 ms stretched the collectives of
+    a 12.5 ms step to 19.9 ms (measured, configs[2] on 8 B200s: the host threads that enqueue them were held up)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, world=1, rank=0):
+        self.period = float(os.environ.get("CFK_CLOCK_PERIOD_MS", "5" if world == 1 else "25")) * 1e-3
         self.sm, self.mx, self.reasons, self.index = [], [], set(), index
+        self.indices = [index] if world == 1 else list(range(world))  # one node: local ranks 0..world-1
+        self.active = rank == 0
         self.stop, self.source = threading.Event(), "nvml"
         self.th = threading.Thread(target=self._run, daemon=True)
 
-    def _nvml_handle(self):
+    def _nvml_handle(self, idx=None):
         import pynvml
         pynvml.nvmlInit()
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        idx = self.index
+        idx = self.index if idx is None else idx
         if vis:
             ent = vis.split(",")[idx].strip()
             if ent.isdigit():
@@ -131,8 +136,11 @@ class ClockSampler:
 
     def _run(self):
         try:
-            nv, h = self._nvml_handle()
-            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            handles = [self._nvml_handle(i) for i in self.indices]
+            nv = handles[0][0]
+            handles = [h for _, h in handles]
+            for h in handles:
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
             bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
                     else nv.nvmlClocksThrottleReasonHwSlowdown,
                     "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
@@ -141,12 +149,13 @@ class ClockSampler:
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
                 nv.nvmlDeviceGetCurrentClocksThrottleReasons
             while not self.stop.is_set():
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                r = int(get_reasons(h))
-                for name, bit in bits.items():
-                    if r & int(bit):
-                        self.reasons.add(name)
-                self.stop.wait(0.005)
+                for h in handles:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = int(get_reasons(h))
+                    for name, bit in bits.items():
+                        if r & int(bit):
+                            self.reasons.add(name)
+                self.stop.wait(self.period)
             return
         except Exception as e:  # noqa: BLE001 - any NVML problem: poll nvidia-smi instead
             self.source = f"nvidia-smi ({type(e).__name__})"
@@ -168,16 +177,19 @@ class ClockSampler:
             self.stop.wait(0.05)
 
     def __enter__(self):
-        self.th.start()
+        if self.active:
+            self.th.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.th.join(timeout=6)
+        if self.active:
+            self.th.join(timeout=6)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
-                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source,
+                "gpus_sampled": len(self.indices), "period_ms": self.period * 1e3}
 
 
 def ncu_traffic(kernel):
@@ -381,7 +393,7 @@ def run_recruit(args):
 
     step_ms, launches0 = [], eng.launch_count()
     stage_ms = {}
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, world, rank) as clk:
         for _ in range(args.steps):
             flush.fill_(1)  # evict L2 between timed steps (inputs alone would fit the 126 MB L2)
             barrier()
@@ -613,7 +625,7 @@ def run_stream(args):
     # of records + 38 MB of packed reads) is several times the 126 MB L2.
     stage_ms, bases, kmers = {}, 0, 0
     launches0 = eng.launch_count()
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, world, rank) as clk:
         flush.fill_(1)
         barrier()
         eng.events = []
