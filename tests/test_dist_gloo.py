@@ -76,6 +76,42 @@ def _worker(rank, world, port, out_dir):
         want_rare = gk[(gm <= max_nonuniq) & (gr >= lo) & (gr <= hi)]
         assert rare.size > 50 and np.array_equal(rare, want_rare)
 
+        # --- the default stage-A exchange: all-to-all of per-read records by partition range -------------------------------
+        # what cfk_docfreq_emit produces is restated with numpy (one record per distinct k-mer of a read, bit 63 = seen
+        # twice in that read, partition = hash range); the exchange itself is the product code (cdist.exchange_records)
+        n_parts = 6 * world
+        my_codes = c_oracle.unpacked_codes(my_batch)
+        recs = []
+        for r in range(my_batch.n_reads):
+            seq = my_codes[int(my_batch.read_off[r]): int(my_batch.read_off[r]) + int(my_batch.read_len[r])].astype(np.uint64)
+            km = np.zeros(seq.size - k + 1, dtype=np.uint64)
+            for j in range(k):
+                km = (km << np.uint64(2)) | seq[j: seq.size - k + 1 + j]
+            u, c = np.unique(km, return_counts=True)
+            recs.append(u | ((c > 1).astype(np.uint64) << np.uint64(63)))
+        recs = np.concatenate(recs)
+        key_bits = np.uint64((1 << 62) - 1)
+        part = (cdist.mix64_np(recs & key_bits) % np.uint64(n_parts)).astype(np.int64)
+        by_part = np.argsort(part, kind="stable")
+        send = torch.from_numpy(recs[by_part].view(np.int64))
+        counts = torch.from_numpy(np.bincount(part, minlength=n_parts).astype(np.int32))
+        recv, recv_counts, flags, n_sent = cdist.exchange_records(send, counts, world, flags=torch.tensor([rank, 0, 7 + rank]))
+        assert flags == [world - 1, 0, 7 + world - 1] and n_sent == recs.size
+        per = n_parts // world
+        got = recv[: int(recv_counts.sum())].numpy().view(np.uint64)
+        offsets = np.concatenate([[0], np.cumsum(recv_counts.numpy().astype(np.int64))])
+        # source-major layout: run (s, q) = the records of local partition q sent by rank s, all of partition rank * per + q
+        for s_ in range(world):
+            for q in range(per):
+                run = got[offsets[s_ * per + q]: offsets[s_ * per + q + 1]]
+                assert ((cdist.mix64_np(run & key_bits) % np.uint64(n_parts)) == np.uint64(rank * per + q)).all()
+        keys_o, inv = np.unique(got & key_bits, return_inverse=True)
+        nr_o = np.bincount(inv, minlength=keys_o.size)
+        nm_o = np.bincount(inv, weights=(got >> np.uint64(63)).astype(np.float64), minlength=keys_o.size).astype(np.int64)
+        mine_rare = keys_o[(nm_o <= max_nonuniq) & (nr_o >= lo) & (nr_o <= hi)]
+        all_rare, _ = cdist.all_gather_v(torch.from_numpy(np.sort(mine_rare).view(np.int64)))
+        assert np.array_equal(np.sort(all_rare.numpy().view(np.uint64)), want_rare)
+
         # --- nominate-then-sum (ShardedRecruiter.global_rare_keys): same rare set for ~1 % of the traffic --------------
         import torch.distributed as tdist
         for lo2, hi2 in ((3, 12), (4, 9), (7, 40)):
