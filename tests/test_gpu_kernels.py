@@ -443,3 +443,49 @@ def test_cloud_build_with_index_filter(eng):
     assert a.n_entries == b.n_entries > 0
     assert np.array_equal(a.unit_ptr.cpu().numpy(), b.unit_ptr.cpu().numpy())
     assert np.array_equal(a.ids.cpu().numpy(), b.ids.cpu().numpy())
+
+
+def test_stream_launch_finish_equals_synchronous_call(eng):
+    """docfreq_stream_launch / docfreq_stream_finish (the streaming bench enqueues batch i + 1 before reading batch i's
+    counters back): same rare keys and the same table as the synchronous docfreq_stream, also when the first launch
+    finds its partition buffers too small and is repeated."""
+    import torch
+    from centroflye_b200.ingest import pack_reads
+    rng = np.random.default_rng(12)
+    batches = []
+    for b in range(3):
+        codes = [_repetitive_read(rng, int(rng.integers(6000, 50000)), int(rng.integers(200, 2100)), 0.05) for _ in range(40)]
+        batches.append(pack_reads(codes, [f"b{b}r{i}" for i in range(len(codes))]))
+    k, band = 17, (3, 30, 3)
+    old = (eng.docfreq_mode, dict(eng.part_cap_seen), eng.part_slack)
+    eng.docfreq_mode = "stream"
+    try:
+        want = []
+        for batch in batches:
+            rare, table = eng.docfreq_stream(eng.upload_reads(batch, k), k, band=band, want_table=True)
+            keys, nr, nm = eng.table_select(table, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)
+            o = np.argsort(keys.cpu().numpy().view(np.uint64))
+            want.append((np.sort(rare.cpu().numpy().view(np.uint64)), keys.cpu().numpy().view(np.uint64)[o],
+                         nr.cpu().numpy()[o], nm.cpu().numpy()[o]))
+        eng.part_cap_seen.clear()
+        eng.part_slack = 0.05  # the first launches overflow and are repeated inside finish()
+        n_max = max(int(b.n_bases) for b in batches)
+        bufs = [torch.empty(2 * n_max, dtype=torch.int64, device=eng.device) for _ in range(2)]
+        handles, got = [], []
+        for i, batch in enumerate(batches):
+            handles.append(eng.docfreq_stream_launch(eng.upload_reads(batch, k), k, band=band, table_buf=bufs[i & 1]))
+            if i >= 1:
+                got.append(eng.docfreq_stream_finish(handles[i - 1]))
+                rare, table = got[-1]
+                keys, nr, nm = eng.table_select(table, 0, 0xFFFFFFFF, 0xFFFFFFFF, with_counts=True)
+                o = np.argsort(keys.cpu().numpy().view(np.uint64))
+                w = want[i - 1]
+                assert np.array_equal(np.sort(rare.cpu().numpy().view(np.uint64)), w[0])
+                assert np.array_equal(keys.cpu().numpy().view(np.uint64)[o], w[1])
+                assert np.array_equal(nr.cpu().numpy()[o], w[2]) and np.array_equal(nm.cpu().numpy()[o], w[3])
+        rare, table = eng.docfreq_stream_finish(handles[-1])
+        assert np.array_equal(np.sort(rare.cpu().numpy().view(np.uint64)), want[-1][0]) and table.cap == want[-1][1].size
+    finally:
+        eng.docfreq_mode, eng.part_slack = old[0], old[2]
+        eng.part_cap_seen.clear()
+        eng.part_cap_seen.update(old[1])
