@@ -61,7 +61,7 @@ SIGNATURES = {
     "cfk_id_histogram": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "cfk_cloud_filter_count": (_int, [_p, _p, _i64, _p, _i64, _i64, _p, _p]),
     "cfk_cloud_filter_write": (_int, [_p, _p, _i64, _p, _i64, _i64, _p, _p, _p]),
-    "cfk_occ_fill": (_int, [_p, _p, _i64, _i64, _p, _p, _p, _p]),
+    "cfk_occ_fill": (_int, [_p, _p, _i64, _i64, _p, _i64, _p, _p, _p]),
     "cfk_occ_sort": (_int, [_p, _p, _i64, _p]),
     "cfk_occ_last": (_int, [_p, _i64, _p, _p, _p]),
     "cfk_unit_splits": (_int, [_p, _p, _i64, _i64, _i64, _p, _p]),

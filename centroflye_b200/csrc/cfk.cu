@@ -1234,17 +1234,20 @@ __global__ void cloud_filter_write_kernel(const int64_t* __restrict__ unit_ptr, 
   }
 }
 
+// cursor[a] starts at occ_ptr[a] (the list lengths sum to the number of cloud entries, < 2^32), so that filling an
+// occurrence is one atomic and one store -- no second random load of occ_ptr[id]
+__global__ void occ_cursor_kernel(const int64_t* __restrict__ occ_ptr, int64_t n_kmers, uint32_t* __restrict__ cursor) {
+  const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < n_kmers) cursor[a] = (uint32_t)occ_ptr[a];
+}
+
 __global__ void occ_fill_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
-                                int64_t unit_lo, int64_t unit_hi, const int64_t* __restrict__ occ_ptr,
-                                int32_t* cursor, uint32_t* occ) {
+                                int64_t unit_lo, int64_t unit_hi, uint32_t* cursor, uint32_t* occ) {
   const int64_t u = unit_lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (u >= unit_hi) return;
   const int lane = threadIdx.x & 31;
   const int64_t e1 = unit_ptr[u + 1];
-  for (int64_t e = unit_ptr[u] + lane; e < e1; e += 32) {
-    uint32_t id = ids[e];
-    occ[occ_ptr[id] + atomicAdd(cursor + id, 1)] = (uint32_t)u;
-  }
+  for (int64_t e = unit_ptr[u] + lane; e < e1; e += 32) occ[atomicAdd(cursor + __ldg(ids + e), 1u)] = (uint32_t)u;
 }
 
 __global__ void occ_sort_kernel(const int64_t* __restrict__ occ_ptr, uint32_t* occ, int64_t n_kmers) {
@@ -2705,11 +2708,13 @@ int cfk_cloud_filter_write(const int64_t* unit_ptr, const uint32_t* ids, int64_t
 }
 
 int cfk_occ_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, int64_t unit_hi,
-                 const int64_t* occ_ptr, int32_t* cursor, uint32_t* occ, cfk_stream_t stream) {
-  if (unit_lo < 0 || unit_hi < unit_lo) return fail(CFK_ERR_INVALID, "cfk_occ_fill: bad unit range");
-  if (unit_hi == unit_lo) return CFK_OK;
+                 const int64_t* occ_ptr, int64_t n_kmers, uint32_t* cursor, uint32_t* occ, cfk_stream_t stream) {
+  if (unit_lo < 0 || unit_hi < unit_lo || n_kmers < 0) return fail(CFK_ERR_INVALID, "cfk_occ_fill: bad unit range");
+  if (unit_hi == unit_lo || n_kmers == 0) return CFK_OK;
+  occ_cursor_kernel<<<(unsigned)blocks_for(n_kmers, 256), 256, 0, (cudaStream_t)stream>>>(occ_ptr, n_kmers, cursor);
+  CFK_CHECK_LAUNCH("occ_cursor_kernel", 1);
   occ_fill_kernel<<<(unsigned)blocks_for((unit_hi - unit_lo) * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      unit_ptr, ids, unit_lo, unit_hi, occ_ptr, cursor, occ);
+      unit_ptr, ids, unit_lo, unit_hi, cursor, occ);
   CFK_CHECK_LAUNCH("occ_fill_kernel", 1);
   return CFK_OK;
 }

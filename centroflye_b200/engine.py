@@ -694,9 +694,11 @@ class Engine:
         mult = self.id_histogram(csr, n_kmers, unit_lo, unit_hi)
         occ_ptr = self.exclusive_scan(mult[:n_kmers]) if n_kmers else self._zeros(1, t.int64)
         n_occ = int(occ_ptr[n_kmers].item()) if n_kmers else 0
+        if n_occ >= 1 << 32:
+            raise CfkError("occurrence lists: 2^32 or more cloud entries")
         occ = self._empty(n_occ, t.int32)
-        cursor = self._zeros(n_kmers, t.int32)
-        _lib.call("cfk_occ_fill", self._p(csr.unit_ptr), self._p(csr.ids), unit_lo, unit_hi, self._p(occ_ptr),
+        cursor = self._empty(n_kmers, t.int32)
+        _lib.call("cfk_occ_fill", self._p(csr.unit_ptr), self._p(csr.ids), unit_lo, unit_hi, self._p(occ_ptr), n_kmers,
                   self._p(cursor), self._p(occ), self._stream())
         _lib.call("cfk_occ_sort", self._p(occ_ptr), self._p(occ), n_kmers, self._stream())
         occ_last = None

@@ -311,10 +311,10 @@ int cfk_cloud_filter_write(const int64_t* unit_ptr, const uint32_t* ids, int64_t
 
 /* ---- stage C/D: unit-distance k-mer pair graph -------------------------------------------
  * Occurrence lists (the inverted cloud CSR): occ[occ_ptr[a] ...] = sorted global unit indices
- * whose cloud contains id a.  occ_ptr = exclusive scan of the cfk_id_histogram output;
- * cursor zeroed by the caller. */
+ * whose cloud contains id a.  occ_ptr = exclusive scan of the cfk_id_histogram output (int64[n_kmers + 1],
+ * occ_ptr[n_kmers] < 2^32); cursor = uint32[n_kmers] of scratch (any contents). */
 int cfk_occ_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, int64_t unit_hi,
-                 const int64_t* occ_ptr, int32_t* cursor, uint32_t* occ, cfk_stream_t stream);
+                 const int64_t* occ_ptr, int64_t n_kmers, uint32_t* cursor, uint32_t* occ, cfk_stream_t stream);
 int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_stream_t stream);
 /* occ_last[i] = unit_last[occ[i]]: the last unit of the read of every occurrence, laid out like occ
  * itself, so that cfk_pair_sketch / cfk_pair_join stream it instead of chasing unit_last[g]. */
