@@ -63,6 +63,8 @@ SIGNATURES = {
     "cfk_cloud_filter_write": (_int, [_p, _p, _i64, _p, _i64, _i64, _p, _p, _p]),
     "cfk_occ_fill": (_int, [_p, _p, _i64, _i64, _p, _i64, _p, _p, _p]),
     "cfk_occ_sort": (_int, [_p, _p, _i64, _p]),
+    "cfk_occ_slice_histogram": (_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
+    "cfk_occ_slice_fill": (_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p]),
     "cfk_occ_last": (_int, [_p, _i64, _p, _p, _p]),
     "cfk_unit_splits": (_int, [_p, _p, _i64, _i64, _i64, _p, _p]),
     "cfk_pair_candidates": (_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _u32, _p, _i64, _p,

@@ -1186,6 +1186,14 @@ __global__ void cloud_compact_kernel(const uint32_t* __restrict__ tmp_ids, const
 }
 
 // ---- multiplicity histogram / filter / occurrence lists (warp per unit) ----------------------
+__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* __restrict__ v, int64_t lo, int64_t hi, int64_t x) {
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)__ldg(v + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void id_histogram_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids,
                                     int64_t unit_lo, int64_t unit_hi, int32_t* mult) {
   const int64_t u = unit_lo + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -1250,6 +1258,24 @@ __global__ void occ_fill_kernel(const int64_t* __restrict__ unit_ptr, const uint
   for (int64_t e = unit_ptr[u] + lane; e < e1; e += 32) occ[atomicAdd(cursor + __ldg(ids + e), 1u)] = (uint32_t)u;
 }
 
+// The same two passes for the ids of [id_lo, id_hi) only (the lists inside a unit are sorted: two binary searches bound
+// the slice): with G GPUs every rank inverts 1/G of the id space of the all-gathered clouds and the lists are
+// all-gathered, instead of every rank inverting everything.  mult / cursor / occ_ptr are indexed by id - id_lo.
+template <bool FILL>
+__global__ void occ_slice_kernel(const int64_t* __restrict__ unit_ptr, const uint32_t* __restrict__ ids, int64_t n_units,
+                                 int64_t id_lo, int64_t id_hi, int32_t* mult, uint32_t* cursor, uint32_t* occ) {
+  const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;  // half a warp per unit
+  if (u >= n_units) return;
+  const int lane = threadIdx.x & 15;
+  const int64_t b = __ldg(unit_ptr + u), e = __ldg(unit_ptr + u + 1);
+  const int64_t e0 = lower_bound_u32(ids, b, e, id_lo), e1 = lower_bound_u32(ids, e0, e, id_hi);
+  for (int64_t i = e0 + lane; i < e1; i += 16) {
+    const int64_t a = (int64_t)__ldg(ids + i) - id_lo;
+    if (FILL) occ[atomicAdd(cursor + a, 1u)] = (uint32_t)u;
+    else atomicAdd(mult + a, 1);
+  }
+}
+
 __global__ void occ_sort_kernel(const int64_t* __restrict__ occ_ptr, uint32_t* occ, int64_t n_kmers) {
   const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= n_kmers) return;
@@ -1260,14 +1286,6 @@ __global__ void occ_sort_kernel(const int64_t* __restrict__ occ_ptr, uint32_t* o
     while (j >= 0 && occ[b + j] > v) { occ[b + j + 1] = occ[b + j]; --j; }
     occ[b + j + 1] = v;
   }
-}
-
-__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* __restrict__ v, int64_t lo, int64_t hi, int64_t x) {
-  while (lo < hi) {
-    int64_t mid = (lo + hi) >> 1;
-    if ((int64_t)__ldg(v + mid) < x) lo = mid + 1; else hi = mid;
-  }
-  return lo;
 }
 
 // usplit[7 u + j - 1] = position of the first id >= (n_kmers * j) >> 3 in unit u's sorted list, j = 1..7:
@@ -2716,6 +2734,28 @@ int cfk_occ_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, 
   occ_fill_kernel<<<(unsigned)blocks_for((unit_hi - unit_lo) * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       unit_ptr, ids, unit_lo, unit_hi, cursor, occ);
   CFK_CHECK_LAUNCH("occ_fill_kernel", 1);
+  return CFK_OK;
+}
+
+int cfk_occ_slice_histogram(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, int64_t id_lo, int64_t id_hi,
+                            int32_t* mult, cfk_stream_t stream) {
+  if (n_units < 0 || id_lo < 0 || id_hi < id_lo || id_hi > (1ll << 32)) return fail(CFK_ERR_INVALID, "cfk_occ_slice_histogram: bad sizes");
+  if (n_units == 0 || id_hi == id_lo) return CFK_OK;
+  occ_slice_kernel<false><<<(unsigned)blocks_for(n_units * 16, 256), 256, 0, (cudaStream_t)stream>>>(
+      unit_ptr, ids, n_units, id_lo, id_hi, mult, nullptr, nullptr);
+  CFK_CHECK_LAUNCH("occ_slice_kernel<histogram>", 1);
+  return CFK_OK;
+}
+
+int cfk_occ_slice_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, int64_t id_lo, int64_t id_hi,
+                       const int64_t* occ_ptr, uint32_t* cursor, uint32_t* occ, cfk_stream_t stream) {
+  if (n_units < 0 || id_lo < 0 || id_hi < id_lo || id_hi > (1ll << 32)) return fail(CFK_ERR_INVALID, "cfk_occ_slice_fill: bad sizes");
+  if (n_units == 0 || id_hi == id_lo) return CFK_OK;
+  occ_cursor_kernel<<<(unsigned)blocks_for(id_hi - id_lo, 256), 256, 0, (cudaStream_t)stream>>>(occ_ptr, id_hi - id_lo, cursor);
+  CFK_CHECK_LAUNCH("occ_cursor_kernel", 1);
+  occ_slice_kernel<true><<<(unsigned)blocks_for(n_units * 16, 256), 256, 0, (cudaStream_t)stream>>>(
+      unit_ptr, ids, n_units, id_lo, id_hi, nullptr, cursor, occ);
+  CFK_CHECK_LAUNCH("occ_slice_kernel<fill>", 1);
   return CFK_OK;
 }
 

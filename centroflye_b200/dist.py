@@ -17,6 +17,8 @@ The reference is single-process; this is the partitioning of SUR
 The collectives are written against torch.distributed only (all_to_all_single, all_gather_into_tensor), so the
 exchange logic below runs unchanged on gloo/CPU tensors (tests/test_dist_gloo.py) and NCCL/CUDA tensors.
 """
+import os
+
 import numpy as np
 
 from . import _lib
@@ -210,6 +212,7 @@ class ShardedRecruiter:
         self.last_increments = 0
         self.bytes_exchanged = 0
         self.nominate = True  # stage A exchange: nominate-then-sum (False: all-to-all of every table record)
+        self.shard_occurrences = os.environ.get("CFK_SHARD_OCC", "1") != "0"  # False: every rank inverts all clouds
 
     # ---- stage A exchange ---------------------------------------------------------------------------------
     def global_rare_stream(self, lo, hi, max_nonuniq):
@@ -321,6 +324,28 @@ class ShardedRecruiter:
         unit_ptr = eng.exclusive_scan(cnt_all) if n_units else eng._zeros(1, t.int64)
         return CloudCSR(unit_ptr=unit_ptr, ids=ids_all, n_units=n_units, n_entries=int(ids_all.numel())), unit_last
 
+    # ---- stage C prologue ---------------------------------------------------------------------------------
+    def global_occurrences(self, gcsr, unit_last, n_kmers):
+        """The occurrence lists of the all-gathered clouds, built once over all ranks instead of once per rank: rank r
+        inverts the ids of [n r / G, n (r + 1) / G) (two binary searches per unit bound its slice of the sorted list),
+        the list lengths and the lists are all-gathered in rank order = id order.  One host sync (every rank's number of
+        occurrences).  -> (occ_ptr, occ, occ_last) as Engine.build_occurrences returns them."""
+        eng, t, W = self.eng, self.torch, self.world
+        bounds = [n_kmers * i // W for i in range(W + 1)]
+        lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        mult, ptr = eng.occurrence_slice_count(gcsr, lo, hi)
+        totals = t.empty(W, dtype=t.int64, device=eng.device)
+        self.dist.all_gather_into_tensor(totals, ptr[hi - lo: hi - lo + 1].contiguous(), group=self.group)
+        totals = [int(c) for c in totals.cpu().tolist()]
+        if sum(totals) >= 1 << 32:
+            raise CfkError("occurrence lists: 2^32 or more cloud entries")
+        occ = eng.occurrence_slice_fill(gcsr, lo, hi, ptr, totals[self.rank])
+        mult_all, _ = all_gather_v(mult.contiguous(), self.group, counts=[bounds[i + 1] - bounds[i] for i in range(W)])
+        occ_all, _ = all_gather_v(occ.contiguous(), self.group, counts=totals)
+        self.bytes_exchanged += 4 * (hi - lo) + 4 * totals[self.rank]
+        occ_ptr = eng.exclusive_scan(mult_all) if n_kmers else eng._zeros(1, t.int64)
+        return occ_ptr, occ_all, eng.occurrence_last(occ_all, unit_last)
+
     # ---- whole path ---------------------------------------------------------------------------------------
     def step(self, lo, hi, max_nonuniq, min_d, max_d, min_cov, rel_threshold=0.8, gather=True, on_clouds=None):
         """-> (index, local CloudCSR, DistResult); with gather=True every rank ends up with all edges / endpoints.
@@ -342,8 +367,12 @@ class ShardedRecruiter:
             on_clouds(index, csr)
         with eng._stage("gather_clouds"):
             gcsr, unit_last = self.global_clouds(csr)
+        occurrences = None
+        if self.shard_occurrences and index.n and gcsr.n_entries:
+            with eng._stage("occurrences"):
+                occurrences = self.global_occurrences(gcsr, unit_last, index.n)
         res = eng.dist_edges(gcsr, unit_last, index.n, min_d, max_d, min_cov, rel_threshold,
-                             a_begin=self.rank, a_stride=self.world)
+                             a_begin=self.rank, a_stride=self.world, occurrences=occurrences)
         stats = t.tensor([res.n_increments, res.n_candidates, res.n_pair_candidates, res.n_splits], dtype=t.int64,
                          device=eng.device)
         self.dist.all_reduce(stats, group=self.group)

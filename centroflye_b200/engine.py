@@ -701,11 +701,41 @@ class Engine:
         _lib.call("cfk_occ_fill", self._p(csr.unit_ptr), self._p(csr.ids), unit_lo, unit_hi, self._p(occ_ptr), n_kmers,
                   self._p(cursor), self._p(occ), self._stream())
         _lib.call("cfk_occ_sort", self._p(occ_ptr), self._p(occ), n_kmers, self._stream())
-        occ_last = None
-        if unit_last is not None and self.use_occ_last:
-            occ_last = self._empty(n_occ, t.int32)
-            _lib.call("cfk_occ_last", self._p(occ), n_occ, self._p(unit_last), self._p(occ_last), self._stream())
-        return occ_ptr, occ, occ_last
+        return occ_ptr, occ, self.occurrence_last(occ, unit_last)
+
+    def occurrence_slice_count(self, csr, id_lo, id_hi):
+        """First half of inverting the ids of [id_lo, id_hi) only (ShardedRecruiter.global_occurrences): -> (mult
+        int32[id_hi - id_lo], ptr int64[id_hi - id_lo + 1] = its exclusive scan); nothing is read back."""
+        t = self.torch
+        n = id_hi - id_lo
+        if n == 0:
+            return self._empty(0, t.int32)[:0], self._zeros(1, t.int64)
+        mult = self._zeros(n, t.int32)
+        _lib.call("cfk_occ_slice_histogram", self._p(csr.unit_ptr), self._p(csr.ids), csr.n_units, id_lo, id_hi,
+                  self._p(mult), self._stream())
+        return mult, self.exclusive_scan(mult)
+
+    def occurrence_slice_fill(self, csr, id_lo, id_hi, ptr, n_occ):
+        """Second half: the slice's occurrence lists back to back (n_occ = ptr[-1], read back by the caller), each sorted."""
+        t = self.torch
+        n = id_hi - id_lo
+        occ = self._empty(n_occ, t.int32)
+        if n == 0 or n_occ == 0:
+            return occ[:n_occ]
+        cursor = self._empty(n, t.int32)
+        _lib.call("cfk_occ_slice_fill", self._p(csr.unit_ptr), self._p(csr.ids), csr.n_units, id_lo, id_hi, self._p(ptr),
+                  self._p(cursor), self._p(occ), self._stream())
+        _lib.call("cfk_occ_sort", self._p(ptr), self._p(occ), n, self._stream())
+        return occ[:n_occ]
+
+    def occurrence_last(self, occ, unit_last):
+        """occ_last[i] = unit_last[occ[i]] (None when the engine is told not to keep the per-occurrence copy)."""
+        if unit_last is None or not self.use_occ_last:
+            return None
+        n_occ = int(occ.numel())
+        occ_last = self._empty(n_occ, self.torch.int32)
+        _lib.call("cfk_occ_last", self._p(occ), n_occ, self._p(unit_last), self._p(occ_last), self._stream())
+        return occ_last
 
     def dist_edges(self, csr, unit_last, n_kmers, min_d, max_d, min_cov, rel_threshold=0.8,
                    unit_lo=0, unit_hi=None, a_begin=0, a_end=None, a_stride=1, occurrences=None):

@@ -316,6 +316,14 @@ int cfk_cloud_filter_write(const int64_t* unit_ptr, const uint32_t* ids, int64_t
 int cfk_occ_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t unit_lo, int64_t unit_hi,
                  const int64_t* occ_ptr, int64_t n_kmers, uint32_t* cursor, uint32_t* occ, cfk_stream_t stream);
 int cfk_occ_sort(const int64_t* occ_ptr, uint32_t* occ, int64_t n_kmers, cfk_stream_t stream);
+/* The same inversion for the ids of [id_lo, id_hi) only, over all n_units units (multi-GPU: rank r inverts its 1/G of the
+ * id space of the all-gathered clouds, the lists are all-gathered in rank order = id order).  mult (zeroed by the
+ * caller), occ_ptr (exclusive scan of mult, int64[id_hi - id_lo + 1]) and cursor (scratch) are indexed by id - id_lo;
+ * the lists inside a unit must be sorted (they are: cfk_cloud_build).  cfk_occ_sort then sorts the slice's lists. */
+int cfk_occ_slice_histogram(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, int64_t id_lo, int64_t id_hi,
+                            int32_t* mult, cfk_stream_t stream);
+int cfk_occ_slice_fill(const int64_t* unit_ptr, const uint32_t* ids, int64_t n_units, int64_t id_lo, int64_t id_hi,
+                       const int64_t* occ_ptr, uint32_t* cursor, uint32_t* occ, cfk_stream_t stream);
 /* occ_last[i] = unit_last[occ[i]]: the last unit of the read of every occurrence, laid out like occ
  * itself, so that cfk_pair_sketch / cfk_pair_join stream it instead of chasing unit_last[g]. */
 int cfk_occ_last(const uint32_t* occ, int64_t n, const uint32_t* unit_last, uint32_t* occ_last, cfk_stream_t stream);

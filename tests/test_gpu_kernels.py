@@ -192,6 +192,42 @@ def test_dist_sharded_by_source_equals_whole(eng):
     assert parts == whole and total_incr == incr
 
 
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_occurrence_slices_concatenate_to_the_whole_inversion(eng, world):
+    """What ShardedRecruiter.global_occurrences all-gathers: the lists of id slice r, in rank order, are the lists of
+    Engine.build_occurrences (ragged clouds; ids absent from every cloud; more ranks than some slices have ids)."""
+    from centroflye_b200.engine import CloudCSR
+    rng = np.random.default_rng(11 + world)
+    for n_kmers in (5, 333, 4000):
+        units = [[np.sort(rng.choice(n_kmers, size=rng.integers(0, min(n_kmers, 150)), replace=False))
+                  for _ in range(rng.integers(1, 12))] for _ in range(30)]
+        ptr, ids, last = _csr_from_units(units, n_kmers)
+        csr = CloudCSR(unit_ptr=eng._to_dev(ptr), ids=eng._to_dev(ids.view(np.int32)), n_units=len(last),
+                       n_entries=int(ids.size))
+        dlast = eng._to_dev(last)
+        occ_ptr, occ, occ_last = eng.build_occurrences(csr, n_kmers, unit_last=dlast)
+        want_ptr, want_occ = occ_ptr.cpu().numpy(), occ.cpu().numpy()
+        # independent restatement: unit indices holding id a, ascending
+        lists = [[] for _ in range(n_kmers)]
+        for u in range(len(last)):
+            for a in ids[ptr[u]: ptr[u + 1]]:
+                lists[int(a)].append(u)
+        assert want_occ.tolist() == [u for lst in lists for u in lst]
+        assert np.array_equal(np.diff(want_ptr), [len(lst) for lst in lists])
+        mults, occs = [], []
+        for r in range(world):
+            lo, hi = n_kmers * r // world, n_kmers * (r + 1) // world
+            mult, sptr = eng.occurrence_slice_count(csr, lo, hi)
+            n_occ = int(sptr[hi - lo].item())
+            occs.append(eng.occurrence_slice_fill(csr, lo, hi, sptr, n_occ).cpu().numpy())
+            mults.append(mult.cpu().numpy())
+            assert n_occ == int(want_ptr[hi] - want_ptr[lo])
+        assert np.array_equal(np.concatenate(mults), np.diff(want_ptr))
+        assert np.array_equal(np.concatenate(occs), want_occ)
+        assert np.array_equal(eng.occurrence_last(occ, dlast).cpu().numpy(), occ_last.cpu().numpy())
+        assert np.array_equal(occ_last.cpu().numpy(), last[want_occ])
+
+
 def test_table_select_partitions_cover_table(eng):
     from centroflye_b200 import synth
     from centroflye_b200.ingest import batch_from_synth
