@@ -6,7 +6,7 @@ import re
 import subprocess
 import sys
 
-WATCH = ["UBLKCP", "UTMALDG", "SYNCS", "CCTL", "LDGSTS", "LDG", "STG", "LDS", "STS", "ATOMS", "ATOMG", "ATOM", "RED", "BAR",
+WATCH = ["UBLKCP", "UTMALDG", "SYNCS", "CCTL", "LDGSTS", "LDG", "STG", "LDS", "STS", "ATOMS", "ATOMG", "ATOM", "REDG", "BAR",
          "SHFL", "VOTE", "MATCH", "REDUX", "IMAD", "LOP3", "SHF", "POPC", "BREV", "FLO", "LDL", "STL", "HMMA", "UTC"]
 
 
@@ -32,8 +32,8 @@ def main():
             if base == "CCTL" or "PREFETCH" in op:
                 cur["prefetch/CCTL"] += 1
     print(f"# {so}: SASS instruction counts per kernel (static; sm_100a).  UBLKCP = cp.async.bulk (TMA engine), SYNCS = mbarrier,")
-    print("# ATOMS / ATOMG / RED = shared / global atomics, LDL / STL = local-memory (spill) traffic, HMMA / UTC* = tensor cores (none: no contraction here)")
-    cols = ["total", "UBLKCP", "SYNCS", "LDG", "STG", "LDS", "STS", "ATOMS", "ATOMG", "RED", "BAR", "SHFL", "VOTE", "MATCH", "REDUX",
+    print("# ATOMS / ATOMG / REDG = shared / global atomics (REDG: no return value), LDL / STL = local-memory (spill) traffic, HMMA / UTC* = tensor cores (none: no contraction here)")
+    cols = ["total", "UBLKCP", "SYNCS", "LDG", "STG", "LDS", "STS", "ATOMS", "ATOMG", "REDG", "BAR", "SHFL", "VOTE", "MATCH", "REDUX",
             "POPC", "BREV", "CCTL", "LDL", "STL", "HMMA", "UTC"]
     print(f"{'kernel':46s} " + " ".join(f"{c:>6s}" for c in cols))
     for name, c in kernels.items():
