@@ -199,3 +199,26 @@ def test_owner_rule_is_a_partition():
         x ^= x >> 33; x = (x * 0xff51afd7ed558ccd) & m; x ^= x >> 33; x = (x * 0xc4ceb9fe1a85ec53) & m; x ^= x >> 33
         return x
     assert [int(v) for v in mix64_np(keys[:50])] == [mix(int(v)) for v in keys[:50]]
+
+
+@pytest.mark.parametrize("world", [1, 2, 5, 8])
+def test_padded_run_offsets_layout(world):
+    """Every rank's run starts on a RUN_ALIGN boundary, partitions inside a run are back to back, nothing overlaps
+    (ragged counts, empty partitions, empty runs)."""
+    from centroflye_b200.dist import RUN_ALIGN, padded_run_offsets
+    scan = lambda c: torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(c.to(torch.int64), 0)])  # noqa: E731
+    rng = np.random.default_rng(world)
+    for per in (1, 3, 40):
+        counts = rng.integers(0, 50, size=world * per).astype(np.int32)
+        counts[rng.random(counts.size) < 0.3] = 0
+        if world > 1:
+            counts[per: 2 * per] = 0  # rank 1 gets nothing at all
+        off, sizes = padded_run_offsets(torch.from_numpy(counts), world, scan)
+        off, sizes = off.numpy(), sizes.numpy()
+        assert (sizes % RUN_ALIGN == 0).all()
+        run_start = np.concatenate([[0], np.cumsum(sizes)])
+        for g in range(world):
+            c = counts[g * per: (g + 1) * per].astype(np.int64)
+            assert off[g * per] == run_start[g]
+            assert np.array_equal(off[g * per: (g + 1) * per], run_start[g] + np.concatenate([[0], np.cumsum(c)[:-1]]))
+            assert run_start[g] + c.sum() <= run_start[g + 1] < run_start[g] + c.sum() + RUN_ALIGN
