@@ -91,6 +91,7 @@ SIGNATURES = {
     # native edge file writer (host pointers)
     "cfk_writer_last_error": (ctypes.c_char_p, []),
     "cfk_write_edges": (_int, [ctypes.c_char_p, _p, _i64, _i32, _p, _p, _p, _p, _i64, _i32]),
+    "cfk_write_edges_rows": (_int, [ctypes.c_char_p, _p, _i64, _i32, _p, _i64, _i32]),
 }
 
 _lib = None

@@ -90,15 +90,37 @@ class KmerFreqs(Mapping):
 
 class RareKmerSet(set):
     """``set[str]`` of rare k-mers that remembers its sorted device copy (ids = ranks).  Any in-place change of the
-    set drops the device copy: the next consumer rebuilds it from the strings."""
+    set drops the device copy: the next consumer rebuilds it from the strings.
+
+    main() never looks at the strings (every consumer on its path takes the device copy), so there the ~10^6 Python
+    strings are not made up front: ``_cfk_pending`` holds the sorted keys and the first Python-level look at the set
+    (len, iteration, membership, any mutator, ``materialize()``) fills them in.  get_rare_kmers() called by anybody
+    else returns the filled set, as the reference does."""
     _cfk_index = None
     _cfk_k = None
+    _cfk_pending = None
+
+    def materialize(self):
+        if self._cfk_pending is not None:
+            keys, self._cfk_pending = self._cfk_pending, None
+            set.update(self, ints_to_kmers(keys, self._cfk_k))
+        return self
+
+    def __len__(self):
+        return set.__len__(self.materialize())
+
+    def __iter__(self):
+        return set.__iter__(self.materialize())
+
+    def __contains__(self, kmer):
+        return set.__contains__(self.materialize(), kmer)
 
 
 def _dropping_index(name):
     method = getattr(set, name)
 
     def mutate(self, *args, **kwargs):
+        self.materialize()
         self._cfk_index = None
         return method(self, *args, **kwargs)
     mutate.__name__ = name
@@ -108,6 +130,24 @@ def _dropping_index(name):
 for _name in ("add", "discard", "remove", "pop", "clear", "update", "difference_update", "intersection_update",
               "symmetric_difference_update", "__ior__", "__iand__", "__isub__", "__ixor__"):
     setattr(RareKmerSet, _name, _dropping_index(_name))
+
+
+def _filled_first(name):
+    method = getattr(set, name)
+
+    def read(self, *args, **kwargs):
+        return method(self.materialize(), *args, **kwargs)
+    read.__name__ = name
+    return read
+
+
+# the read-only methods of set look at the C-level table directly: fill it first.  (A plain set built FROM a pending
+# RareKmerSet -- set(rare), other | rare -- cannot be intercepted; only main() ever holds a pending one.)
+for _name in ("copy", "union", "intersection", "difference", "symmetric_difference", "issubset", "issuperset",
+              "isdisjoint", "__or__", "__and__", "__sub__", "__xor__", "__ror__", "__rand__", "__rsub__", "__rxor__",
+              "__eq__", "__ne__", "__le__", "__lt__", "__ge__", "__gt__", "__reduce__", "__repr__"):
+    setattr(RareKmerSet, _name, _filled_first(_name))
+RareKmerSet.__hash__ = None  # as for set: defining __eq__ must not make instances hashable
 
 
 class KmerRanks(Mapping):
@@ -139,16 +179,40 @@ class KmerRanks(Mapping):
 
 
 class EdgeList(Sequence):
-    """Edges as the reference's tuples ``(dist, i, j, freq)``, sorted by (dist, i, j), numpy-backed."""
+    """Edges as the reference's tuples ``(dist, i, j, freq)``, sorted by (dist, i, j), numpy-backed.
+
+    Built from four columns, or (``from_rows``) from the device's own rows uint32[n][4] = (i, j, dist, freq): then the
+    int64 columns ``dist`` / ``i`` / ``j`` / ``freq`` are made only if somebody reads them -- the native writer takes
+    the rows as they are."""
 
     def __init__(self, dist, i, j, freq, presorted=False):
         if not presorted:
             order = np.lexsort((j, i, dist))
             dist, i, j, freq = dist[order], i[order], j[order], freq[order]
-        self.dist, self.i, self.j, self.freq = (np.ascontiguousarray(x, dtype=np.int64) for x in (dist, i, j, freq))
+        self.rows = None
+        self._cols = tuple(np.ascontiguousarray(x, dtype=np.int64) for x in (dist, i, j, freq))
+
+    @classmethod
+    def from_rows(cls, rows, presorted=False):
+        rows = np.ascontiguousarray(rows, dtype=np.uint32).reshape(-1, 4)
+        if not presorted:
+            rows = rows[np.lexsort((rows[:, 1], rows[:, 0], rows[:, 2]))]
+        self = cls.__new__(cls)
+        self.rows, self._cols = rows, None
+        return self
+
+    def _columns(self):
+        if self._cols is None:
+            self._cols = tuple(self.rows[:, c].astype(np.int64) for c in (2, 0, 1, 3))
+        return self._cols
+
+    dist = property(lambda self: self._columns()[0])
+    i = property(lambda self: self._columns()[1])
+    j = property(lambda self: self._columns()[2])
+    freq = property(lambda self: self._columns()[3])
 
     def __len__(self):
-        return int(self.dist.size)
+        return int(self.rows.shape[0]) if self._cols is None else int(self._cols[0].size)
 
     def __getitem__(self, n):
         if isinstance(n, slice):
@@ -227,7 +291,8 @@ def get_kmer_freqs_from_ncrf_report(reads_ncrf_report, k, verbose, max_nonuniq):
     return KmerFreqs(to_host_u64(keys), to_host_u32(nreads), k, table=table, engine=engine)
 
 
-def get_rare_kmers(reads_ncrf_report, k, bottom, top, coverage, kmer_survival_rate, max_nonuniq, verbose):
+def get_rare_kmers(reads_ncrf_report, k, bottom, top, coverage, kmer_survival_rate, max_nonuniq, verbose,
+                   _strings=True):
     k = check_k(k)
     engine = default_engine()
     reads = report_device_reads(reads_ncrf_report, engine, k)
@@ -236,11 +301,14 @@ def get_rare_kmers(reads_ncrf_report, k, bottom, top, coverage, kmer_survival_ra
     lo, hi = band_to_int(left, right)
     rare_keys = engine.rare_kmers(reads, k, lo, hi, max_nonuniq)  # counting and band in one device pass
     index = engine.build_index(rare_keys)
-    rare = RareKmerSet(ints_to_kmers(to_host_u64(index.sorted_keys), k))
+    rare = RareKmerSet()
     rare._cfk_index = (engine, index)
     rare._cfk_k = k
+    rare._cfk_pending = to_host_u64(index.sorted_keys)
+    if _strings:
+        rare.materialize()
     if verbose:
-        print(f'# rare kmers: {len(rare)}')
+        print(f'# rare kmers: {index.n}')
     return rare
 
 
@@ -280,8 +348,7 @@ def filter_dist_tuples(dist_cnt, min_coverage, rel_threshold=0.8):
     e = to_host_u32(edges).reshape(-1, 4)
     dist_cnt.n_increments = res.n_increments
     selected_kmers = set(to_host_u32(res.selected).tolist())
-    selected_edges = EdgeList(e[:, 2].astype(np.int64), e[:, 0].astype(np.int64), e[:, 1].astype(np.int64),
-                              e[:, 3].astype(np.int64), presorted=presorted)
+    selected_edges = EdgeList.from_rows(e, presorted=presorted)
     return selected_kmers, selected_edges
 
 
@@ -335,9 +402,13 @@ def write_edges_native(path, kmer_index, dist_edges, threads=0):
     from . import _lib
     lib = _lib.load()
     keys = np.ascontiguousarray(kmer_index.keys_u64, dtype=np.uint64)
-    rc = lib.cfk_write_edges(os.fsencode(path), keys.ctypes.data, int(keys.size), int(kmer_index.k),
-                             dist_edges.dist.ctypes.data, dist_edges.i.ctypes.data, dist_edges.j.ctypes.data,
-                             dist_edges.freq.ctypes.data, len(dist_edges), int(threads))
+    if dist_edges.rows is not None:  # the device's rows, untouched
+        rc = lib.cfk_write_edges_rows(os.fsencode(path), keys.ctypes.data, int(keys.size), int(kmer_index.k),
+                                      dist_edges.rows.ctypes.data, len(dist_edges), int(threads))
+    else:
+        rc = lib.cfk_write_edges(os.fsencode(path), keys.ctypes.data, int(keys.size), int(kmer_index.k),
+                                 dist_edges.dist.ctypes.data, dist_edges.i.ctypes.data, dist_edges.j.ctypes.data,
+                                 dist_edges.freq.ctypes.data, len(dist_edges), int(threads))
     if rc != 0:
         raise OSError(lib.cfk_writer_last_error().decode(errors="replace"))
 
@@ -360,7 +431,8 @@ def main(argv=None):
                                 coverage=params.coverage,
                                 kmer_survival_rate=params.kmer_survival_rate,
                                 max_nonuniq=params.max_nonuniq,
-                                verbose=params.verbose)
+                                verbose=params.verbose,
+                                _strings=False)  # nothing below reads the strings: they are made only if asked for
 
     stamp.append(("ingest_count_rare", time.perf_counter()))
 

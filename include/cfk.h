@@ -446,6 +446,10 @@ void cfk_ncrf_close(cfk_ncrf_t* ctx);
 const char* cfk_writer_last_error(void);
 int cfk_write_edges(const char* path, const uint64_t* keys_sorted_h, int64_t n_keys, int32_t k, const int64_t* dist_h,
                     const int64_t* i_h, const int64_t* j_h, const int64_t* freq_h, int64_t n_edges, int32_t n_threads);
+/* The same file from the rows cfk_pair_join writes, copied to the host as they are: rows_h = uint32[n_edges][4] =
+ * (i, j, dist, cnt).  Spares the caller four strided int64 column copies (80 ms for 8e6 edges). */
+int cfk_write_edges_rows(const char* path, const uint64_t* keys_sorted_h, int64_t n_keys, int32_t k, const uint32_t* rows_h,
+                         int64_t n_edges, int32_t n_threads);
 
 #ifdef __cplusplus
 }

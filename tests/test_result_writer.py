@@ -28,6 +28,45 @@ def test_native_writer_matches_python(tmp_path, k, n_keys, n_edges):
         assert fn.read_bytes() == _python_bytes(ranks, el)
 
 
+@pytest.mark.parametrize("k,n_keys,n_edges", [(5, 300, 1), (19, 5000, 70001), (31, 2000, 1200003), (19, 10, 0)])
+def test_native_writer_from_device_rows(tmp_path, k, n_keys, n_edges):
+    """EdgeList.from_rows keeps the uint32 rows (i, j, dist, freq) of cfk_pair_join; cfk_write_edges_rows writes the same
+    bytes as the column form and as the Python loop; the int64 columns appear only when read.  1.2e6 edges = several
+    batches of the writer's double buffering on any core count."""
+    rng = np.random.default_rng(k + n_edges)
+    keys = np.sort(rng.choice(min(1 << (2 * k), 1 << 40), size=min(n_keys, 1 << (2 * k)), replace=False).astype(np.uint64))
+    ranks = dbkr.KmerRanks(keys, k)
+    n = keys.size
+    rows = np.stack([rng.integers(0, n, n_edges), rng.integers(0, n, n_edges), rng.integers(1, 151, n_edges),
+                     rng.integers(4, 3000, n_edges)], 1).astype(np.uint32)
+    el = dbkr.EdgeList.from_rows(rows)  # sorts by (dist, i, j) on the host
+    assert el._cols is None and len(el) == n_edges
+    by_cols = dbkr.EdgeList(rows[:, 2].astype(np.int64), rows[:, 0].astype(np.int64), rows[:, 1].astype(np.int64),
+                            rows[:, 3].astype(np.int64))
+    for threads in (1, 3, 0):
+        fn = tmp_path / f"rows_{threads}.txt"
+        dbkr.write_edges_native(str(fn), ranks, el, threads=threads)
+        assert el._cols is None  # the writer took the rows as they are
+        fn2 = tmp_path / f"cols_{threads}.txt"
+        dbkr.write_edges_native(str(fn2), ranks, by_cols, threads=threads)
+        assert fn.read_bytes() == fn2.read_bytes()
+    if n_edges <= 100000:
+        assert (tmp_path / "rows_0.txt").read_bytes() == _python_bytes(ranks, el)
+    assert np.array_equal(el.dist, by_cols.dist) and np.array_equal(el.i, by_cols.i)
+    assert np.array_equal(el.j, by_cols.j) and np.array_equal(el.freq, by_cols.freq)
+    if n_edges:
+        assert el[0] == by_cols[0] and list(el)[-1] == by_cols[len(by_cols) - 1]
+    pre = dbkr.EdgeList.from_rows(el.rows, presorted=True)
+    assert pre.rows is not None and np.array_equal(pre.rows, el.rows)
+
+
+def test_native_writer_rows_reject_bad_ids(tmp_path):
+    ranks = dbkr.KmerRanks(np.array([1, 2, 3], dtype=np.uint64), 5)
+    el = dbkr.EdgeList.from_rows(np.array([[0, 3, 1, 4]], dtype=np.uint32))
+    with pytest.raises(OSError, match="outside"):
+        dbkr.write_edges_native(str(tmp_path / "x.txt"), ranks, el)
+
+
 def test_output_results_uses_native_writer_and_sorted_edges(tmp_path):
     rng = np.random.default_rng(3)
     keys = np.sort(rng.choice(1 << 38, size=1000, replace=False).astype(np.uint64))
