@@ -9,9 +9,13 @@
 // fixtures pin to the reference's regex parser (tests/test_ncrf_native.py).
 //
 // Plain host C++ (std::thread over records); linked into libcfk.so so the C ABI stays one library.
+#include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -164,7 +168,15 @@ struct PerRead {
 }  // namespace
 
 struct cfk_ncrf {
+  // the report text: the file mapped read-only (no copy, no zero-filled buffer: 0.1 s of a 320 MB report), or -- what
+  // cannot be mapped (pipes, empty files) -- read into `text`
+  const char* data = nullptr;
+  size_t size = 0;
+  void* mapped = nullptr;
   std::vector<char> text;
+  ~cfk_ncrf() {
+    if (mapped) munmap(mapped, size);
+  }
   std::vector<Record> kept;         // insertion order of the reference's dict
   std::vector<PerRead> per;
   std::vector<int64_t> read_off;    // bases, 64-aligned
@@ -280,23 +292,43 @@ const char* cfk_ncrf_last_error(void) { return g_ingest_err; }
 int cfk_ncrf_open(const char* path, int64_t min_record_len, int32_t n_per_match, int32_t n_threads, cfk_ncrf_t** out) {
   if (!path || !out || n_per_match < 1) return ingest_fail(CFK_ERR_INVALID, "cfk_ncrf_open: bad arguments");
   *out = nullptr;
-  FILE* f = fopen(path, "rb");
-  if (!f) return ingest_fail(CFK_ERR_INVALID, std::string("cfk_ncrf_open: cannot open ") + path);
   std::unique_ptr<cfk_ncrf> ctx(new cfk_ncrf);
-  fseek(f, 0, SEEK_END);
-  const long size = ftell(f);
-  fseek(f, 0, SEEK_SET);
-  ctx->text.resize(size > 0 ? (size_t)size : 0);
-  const size_t got = ctx->text.empty() ? 0 : fread(ctx->text.data(), 1, ctx->text.size(), f);
-  fclose(f);
-  if (got != ctx->text.size()) return ingest_fail(CFK_ERR_INVALID, std::string("cfk_ncrf_open: short read of ") + path);
+  {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return ingest_fail(CFK_ERR_INVALID, std::string("cfk_ncrf_open: cannot open ") + path);
+    struct stat st;
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+      void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m != MAP_FAILED) {
+        ctx->mapped = m;
+        ctx->data = (const char*)m;
+        ctx->size = (size_t)st.st_size;
+        madvise(m, ctx->size, MADV_WILLNEED);
+      }
+    }
+    if (!ctx->mapped) {  // not mappable: read to the end
+      char buf[1 << 16];
+      for (;;) {
+        const ssize_t got = read(fd, buf, sizeof(buf));
+        if (got < 0) {
+          close(fd);
+          return ingest_fail(CFK_ERR_INVALID, std::string("cfk_ncrf_open: short read of ") + path);
+        }
+        if (got == 0) break;
+        ctx->text.insert(ctx->text.end(), buf, buf + got);
+      }
+      ctx->data = ctx->text.data();
+      ctx->size = ctx->text.size();
+    }
+    close(fd);
+  }
   ctx->n_per_match = n_per_match;
   ctx->n_threads = n_threads > 0 ? n_threads : (int)std::max(1u, std::thread::hardware_concurrency());
 
   // lines: strip, drop empty and '#' lines (ncrf_parser.py:65-68), then pair them up
   std::vector<Span> lines;
-  const char* p = ctx->text.data();
-  const char* end = p + ctx->text.size();
+  const char* p = ctx->data;
+  const char* end = p + ctx->size;
   while (p < end) {
     const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
     const char* le = nl ? nl : end;

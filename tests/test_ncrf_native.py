@@ -89,6 +89,28 @@ def test_native_ingest_empty_report(tmp_path):
     assert units.read_unit_ptr.tolist() == [0]
 
 
+def test_native_ingest_reads_what_cannot_be_mapped(tmp_path):
+    """The report is mapped read-only; a FIFO (the reference's open() reads one just as well) and a zero-byte file take
+    the read-to-the-end path and give the same arrays."""
+    import os
+    import threading
+    two = MOTIF * 2
+    text = _record("r_a", two + "ACG", two + "ACG") + "# comment\n" + _record("r_b", "T" + two, "T" + two, strand="-")
+    want, want_units, want_fields = native_ingest(_write(tmp_path, text), min_record_len=0)
+    fifo = str(tmp_path / "report.fifo")
+    os.mkfifo(fifo)
+    feeder = threading.Thread(target=lambda: open(fifo, "w").write(text))
+    feeder.start()
+    got, got_units, got_fields = native_ingest(fifo, min_record_len=0)
+    feeder.join()
+    assert got.r_ids == want.r_ids and np.array_equal(got.packed, want.packed) and np.array_equal(got.read_len, want.read_len)
+    assert np.array_equal(got_units.unit_off, want_units.unit_off) and np.array_equal(got_fields, want_fields)
+    empty = tmp_path / "empty.ncrf"
+    empty.write_bytes(b"")
+    batch, units, _ = native_ingest(str(empty))
+    assert batch.n_reads == 0 and units.n_units == 0
+
+
 def test_native_ingest_errors(tmp_path):
     two = MOTIF * 2
     with pytest.raises(ValueError, match="non-ACGT"):
