@@ -345,7 +345,7 @@ def filter_dist_tuples(dist_cnt, min_coverage, rel_threshold=0.8):
                         "(the counting and the filter are fused on the device)")
     res = dist_cnt.run(min_coverage, rel_threshold)
     edges, presorted = _sort_edges_on_device(res.edges, dist_cnt.state.index.n, dist_cnt.max_d)
-    e = to_host_u32(edges).reshape(-1, 4)
+    e = to_host_u32(edges, pinned=True).reshape(-1, 4)
     dist_cnt.n_increments = res.n_increments
     selected_kmers = set(to_host_u32(res.selected).tolist())
     selected_edges = EdgeList.from_rows(e, presorted=presorted)

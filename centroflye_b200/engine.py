@@ -852,5 +852,14 @@ def to_host_u64(t):
     return t.cpu().numpy().view(np.uint64)
 
 
-def to_host_u32(t):
+def to_host_u32(t, pinned=False):
+    """Device tensor -> numpy uint32 view.  pinned: through a page-locked buffer of its own (the array keeps it alive;
+    torch caches the allocation), 129 MB of edges in ~3 ms instead of ~60 ms through pageable memory."""
+    if pinned and t.is_cuda and t.numel():
+        import torch
+        dst = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        with torch.cuda.device(t.device):
+            dst.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+        return dst.numpy().view(np.uint32)
     return t.cpu().numpy().view(np.uint32)
