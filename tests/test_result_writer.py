@@ -106,3 +106,21 @@ def test_device_edge_sort_matches_host_lexsort(n_kmers, max_d):
         assert np.array_equal(got, e[order])
     else:
         assert np.array_equal(got, e)
+
+
+def test_native_writer_reports_io_errors(tmp_path):
+    """A full device (the write happens on the writer thread, one batch behind the formatting) and a missing directory
+    both surface as OSError with the path in the message; nothing is silently truncated."""
+    import os
+    rng = np.random.default_rng(5)
+    keys = np.sort(rng.choice(1 << 38, size=1000, replace=False).astype(np.uint64))
+    ranks = dbkr.KmerRanks(keys, 19)
+    n = 300000
+    rows = np.stack([rng.integers(0, 1000, n), rng.integers(0, 1000, n), rng.integers(1, 151, n), rng.integers(4, 60, n)],
+                    1).astype(np.uint32)
+    el = dbkr.EdgeList.from_rows(rows)
+    if os.path.exists("/dev/full"):
+        with pytest.raises(OSError, match="short write to /dev/full"):
+            dbkr.write_edges_native("/dev/full", ranks, el, threads=2)
+    with pytest.raises(OSError, match="cannot open"):
+        dbkr.write_edges_native(str(tmp_path / "no_such_dir" / "x.txt"), ranks, el)
