@@ -100,7 +100,10 @@ int write_edge_lines(const char* path, const uint64_t* keys_sorted_h, int64_t n_
     }
     for (auto& th : pool) th.join();
     if (writer.joinable()) writer.join();  // the previous batch is on its way to the file: its buffers are free again
-    if (write_rc != CFK_OK) rc = write_rc;
+    if (write_rc != CFK_OK) {
+      snprintf(g_writer_err, sizeof(g_writer_err), "cfk_write_edges: short write to %s", path);
+      rc = write_rc;
+    }
     for (int t = 0; t < T && rc == CFK_OK; ++t)
       if (bad[(size_t)t]) {
         snprintf(g_writer_err, sizeof(g_writer_err), "cfk_write_edges: k-mer id outside [0, n_keys)");
