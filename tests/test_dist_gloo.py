@@ -37,6 +37,7 @@ def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        import torch.distributed as tdist_mod
         from centroflye_b200 import dist as cdist
         from oracle import c_oracle
 
@@ -161,6 +162,47 @@ def _worker(rank, world, port, out_dir):
         gids = np.ascontiguousarray(ids_all.numpy().view(np.uint32))
         gl = np.ascontiguousarray(unit_last.numpy())
         assert (gl >= np.arange(gl.size)).all() and gl[-1] == gl.size - 1
+        # --- occurrence lists built once over all ranks (ShardedRecruiter.global_occurrences): the orchestration is the
+        # product code, the two device passes are restated with numpy behind the engine's method names -------------------
+        class _SliceEngine:
+            device, torch, use_occ_last = torch.device("cpu"), torch, True
+
+            @staticmethod
+            def exclusive_scan(c):
+                return torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(c.to(torch.int64), 0)])
+
+            @staticmethod
+            def _zeros(n, dtype):
+                return torch.zeros(max(int(n), 1), dtype=dtype)
+
+            def _lists(self, lo, hi):
+                unit_of = np.repeat(np.arange(gptr.size - 1), np.diff(gptr))
+                keep = (gids >= lo) & (gids < hi)
+                order = np.lexsort((unit_of[keep], gids[keep]))
+                return gids[keep][order].astype(np.int64) - lo, unit_of[keep][order]
+
+            def occurrence_slice_count(self, csr, lo, hi):
+                mult = torch.from_numpy(np.bincount(self._lists(lo, hi)[0], minlength=hi - lo).astype(np.int32))
+                return mult, self.exclusive_scan(mult)
+
+            def occurrence_slice_fill(self, csr, lo, hi, ptr, n_occ):
+                occ = self._lists(lo, hi)[1]
+                assert occ.size == n_occ == int(ptr[hi - lo])
+                return torch.from_numpy(occ.astype(np.int32))
+
+            @staticmethod
+            def occurrence_last(occ, unit_last_t):
+                return unit_last_t[occ.to(torch.int64)]
+
+        sr = object.__new__(cdist.ShardedRecruiter)
+        sr.eng, sr.torch, sr.dist, sr.world, sr.rank, sr.group, sr.bytes_exchanged = _SliceEngine(), torch, tdist_mod, world, rank, None, 0
+        occ_ptr, occ, occ_last = sr.global_occurrences(None, unit_last, int(rare.size))
+        unit_of = np.repeat(np.arange(gptr.size - 1), np.diff(gptr))
+        by_id = np.lexsort((unit_of, gids))
+        assert np.array_equal(occ.numpy(), unit_of[by_id])  # every id's units, ascending: the whole inversion
+        assert np.array_equal(np.diff(occ_ptr.numpy()), np.bincount(gids, minlength=rare.size))
+        assert np.array_equal(occ_last.numpy(), gl[unit_of[by_id]])
+
         part = c_oracle.dist_edges(gptr, gids, gl, rare.size, 1, 150, 2)  # all sources, on the global numbering
         e = part["edges"]
         mine_e = e[e[:, 0] % world == rank]  # what this rank's a = rank, rank + G, ... pass would emit
